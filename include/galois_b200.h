@@ -1,0 +1,194 @@
+/*
+ * galois_b200.h — C ABI of the B200-native finite-field backend.
+ *
+ * This is the drop-in boundary: every entry point below replaces one dispatcher
+ * of mhostetter/galois's L2 "UFunc"/"Function" layer (the reference has no FFI of
+ * its own — its "plugin API" is two Python dispatcher classes).
+ * The reference interface each function replaces is cited as file:line under
+ * /root/reference/src/galois/.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, integers; no torch / C++ types cross this boundary.
+ *   - `*_dev` style functions (no suffix) take DEVICE pointers and a `stream`
+ *     (a cudaStream_t cast to void*; NULL = legacy default stream); they are
+ *     asynchronous and never synchronise.
+ *   - `*_host` functions take HOST pointers, run a chunked H2D → kernel → D2H
+ *     pipeline on internal streams and return after the result is in `out`.
+ *   - element storage is native width: elem_bytes ∈ {1,2,4,8} (the reference's
+ *     dtypes uint8/uint16/uint32/int8/int16/int32/int64, _domains/_meta.py:19;
+ *     values are always non-negative so signedness does not matter), or 16 for
+ *     GF(2^m), 64 < m <= 128 (two little-endian uint64 limbs per element; the
+ *     reference holds these as Python ints in dtype=object arrays).
+ *   - every function returns a gfb_status; nothing throws across the boundary.
+ *   - "zero division" (reference: ZeroDivisionError raised from inside the Numba
+ *     loop, _domains/_calculate.py:403-404, _lookup.py:194-195,225-226,261-262)
+ *     is a sticky per-context flag set by the kernel and read with
+ *     gfb_take_error(); `*_host` functions return GFB_ERR_ZERO_DIVISION directly.
+ */
+#ifndef GALOIS_B200_H
+#define GALOIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gfb_status {
+    GFB_OK = 0,
+    GFB_ERR_ZERO_DIVISION = 1, /* inverse of 0 / 0**negative requested            */
+    GFB_ERR_BAD_ARG = 2,       /* unsupported field / dtype / size / null pointer */
+    GFB_ERR_CUDA = 3,          /* a CUDA runtime call failed; see gfb_last_error  */
+    GFB_ERR_UNSUPPORTED = 4    /* valid in the reference, not built here (yet)    */
+} gfb_status;
+
+typedef enum gfb_field_kind {
+    GFB_PRIME = 1,  /* GF(p), p prime, p < 2^32            (_fields/_ufunc.py:20-33)  */
+    GFB_BINARY = 2  /* GF(2^m), 1 <= m <= 128              (_fields/_ufunc.py:56-74)  */
+} gfb_field_kind;
+
+/* Binary ufuncs (UFunc dispatchers, _domains/_ufunc.py:339-441). */
+typedef enum gfb_binop {
+    GFB_ADD = 0, /* add_modular _calculate.py:133-147 / np.bitwise_xor _fields/_ufunc.py:59 */
+    GFB_SUB = 1, /* subtract_modular _calculate.py:235-251 / xor                            */
+    GFB_MUL = 2, /* multiply_modular :327-340, multiply_binary :288-324, lookup _lookup.py:143-168 */
+    GFB_DIV = 3  /* divide _calculate.py:492-513, _lookup.py:201-233; one fused pass        */
+} gfb_binop;
+
+/* Unary ufuncs. */
+typedef enum gfb_unop {
+    GFB_NEG = 0,   /* negative_modular _calculate.py:184-199 / np.positive for GF(2^m) */
+    GFB_INV = 1,   /* reciprocal_modular_egcd :386-417, reciprocal_itoh_tsujii :447-489 */
+    GFB_SQUARE = 2 /* square_ufunc _domains/_ufunc.py:493-503 (x*x)                    */
+} gfb_unop;
+
+typedef struct gfb_field gfb_field;       /* opaque: constants + device tables           */
+typedef struct gfb_ntt_plan gfb_ntt_plan; /* opaque: twiddle tables for one (field,N,ω)  */
+typedef struct gfb_rs_code gfb_rs_code;   /* opaque: RS(n,k) generator/roots on device   */
+
+/* ---------------------------------------------------------------- library ---- */
+/* Number of CUDA devices visible, or 0 (never fails). */
+int gfb_device_count(void);
+/* Human-readable text of the last failing CUDA call on this thread ("" if none). */
+const char* gfb_last_error(void);
+/* Version string "galois_b200 x.y (sm_100a)". */
+const char* gfb_version(void);
+/* Read-and-clear the sticky error flag of `f` after synchronising `stream`.
+ * Returns GFB_OK or GFB_ERR_ZERO_DIVISION. */
+gfb_status gfb_take_error(gfb_field* f, void* stream);
+
+/* Pinned host memory for the `*_host` pipelines (cudaHostAlloc / cudaFreeHost). */
+void* gfb_host_alloc(size_t bytes);
+void gfb_host_free(void* p);
+
+/* ------------------------------------------------------------------ fields ---- */
+/* Replaces FieldArrayMeta/`Array.compile` (_domains/_array.py:322-362) + table build
+ * `_build_lookup_tables` (_domains/_lookup.py:319-371).
+ *   kind=GFB_PRIME : order_lo = p (p < 2^32), degree = 1, poly_* ignored.
+ *   kind=GFB_BINARY: degree = m; poly_lo/poly_hi = low 128 bits of the irreducible
+ *                    polynomial's integer representation INCLUDING x^m when m < 128
+ *                    (for m = 128 the x^128 term is implicit); primitive_element is
+ *                    the generator used for the EXP/LOG tables (m <= 16 only).
+ * The field is bound to the CUDA device current at creation. */
+gfb_status gfb_field_create(gfb_field** out, int kind, uint64_t order_lo, int degree,
+                            uint64_t poly_lo, uint64_t poly_hi, uint64_t primitive_element);
+void gfb_field_destroy(gfb_field* f);
+/* 1 if the EXP/LOG tables are in use (m <= 12: staged in shared memory). */
+int gfb_field_uses_tables(const gfb_field* f);
+
+/* --------------------------------------------------------- element-wise ufuncs */
+/* out[i] = a[i] (op) b[i], i < n.   UFunc.__call__ on two arrays, _ufunc.py:339-441. */
+gfb_status gfb_binary(gfb_field* f, int op, int elem_bytes, const void* a, const void* b,
+                      void* out, size_t n, void* stream);
+/* out[i] = a[i] (op) s   (scalar_on_left=0)   or   s (op) a[i]   (scalar_on_left=1).
+ * s is a field element given as (lo, hi) limbs (hi = 0 unless elem_bytes == 16).
+ * NumPy broadcasting of a 0-d operand, _ufunc.py:391-401. */
+gfb_status gfb_binary_scalar(gfb_field* f, int op, int elem_bytes, const void* a, uint64_t s_lo,
+                             uint64_t s_hi, int scalar_on_left, void* out, size_t n, void* stream);
+/* out[i] = op(a[i]). */
+gfb_status gfb_unary(gfb_field* f, int op, int elem_bytes, const void* a, void* out, size_t n,
+                     void* stream);
+/* out[i] = a[i] ** e[i], e int64 (negative allowed).  power_square_and_multiply
+ * _calculate.py:558-592, power_ufunc.lookup _lookup.py:236-270. */
+gfb_status gfb_power(gfb_field* f, int elem_bytes, const void* a, const int64_t* e, void* out,
+                     size_t n, void* stream);
+/* out[i] = a[i] ** e (one exponent for the whole array). */
+gfb_status gfb_power_scalar(gfb_field* f, int elem_bytes, const void* a, int64_t e, void* out,
+                            size_t n, void* stream);
+
+/* Host-buffer variants: same semantics, pointers are host memory (pinned is faster).
+ * Chunked, double-buffered H2D/compute/D2H on internal streams. */
+gfb_status gfb_binary_host(gfb_field* f, int op, int elem_bytes, const void* a, const void* b,
+                           void* out, size_t n);
+gfb_status gfb_binary_scalar_host(gfb_field* f, int op, int elem_bytes, const void* a,
+                                  uint64_t s_lo, uint64_t s_hi, int scalar_on_left, void* out,
+                                  size_t n);
+gfb_status gfb_unary_host(gfb_field* f, int op, int elem_bytes, const void* a, void* out, size_t n);
+gfb_status gfb_power_host(gfb_field* f, int elem_bytes, const void* a, const int64_t* e, void* out,
+                          size_t n);
+gfb_status gfb_power_scalar_host(gfb_field* f, int elem_bytes, const void* a, int64_t e, void* out,
+                                 size_t n);
+
+/* ----------------------------------------------------------------- NTT / INTT */
+/* Replaces fft_jit / ifft_jit (_domains/_function.py:170-392) behind galois.ntt/intt
+ * (_ntt.py:16-278) for radix-2 sizes over prime fields, and ADDS the batch dimension
+ * the reference lacks (it is 1-D only, _function.py:180-181).
+ *   X[b][k] = scale * sum_j x[b][j] * omega^(j*k)  (mod p), natural order in and out.
+ * `n` must be a power of two, 1 <= n <= 2^24, n | p-1; `omega` a primitive n-th root of
+ * unity chosen by the caller exactly as the reference does (FieldArray.primitive_root_of_unity,
+ * _fields/_array.py:1127-1187; its inverse for INTT, _function.py:194-195); `scale` is 1 or
+ * (n mod p)^-1 (_function.py:209-210). */
+gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint64_t omega,
+                               uint64_t scale);
+void gfb_ntt_plan_destroy(gfb_ntt_plan* plan);
+/* Bytes of device workspace gfb_ntt_exec needs for `batch` transforms (0 if none). */
+size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* plan, int elem_bytes, size_t batch);
+/* x, y: [batch][n] contiguous device arrays of elem_bytes ∈ {4, 8}; y may alias x. */
+gfb_status gfb_ntt_exec(gfb_ntt_plan* plan, int elem_bytes, const void* x, void* y, size_t batch,
+                        void* workspace, void* stream);
+gfb_status gfb_ntt_exec_host(gfb_ntt_plan* plan, int elem_bytes, const void* x, void* y,
+                             size_t batch);
+
+/* -------------------------------------------------- convolution and matmul ---- */
+/* Full linear convolution, out has na + nb - 1 elements.  convolve_jit
+ * (_domains/_function.py:111-167). */
+gfb_status gfb_convolve(gfb_field* f, int elem_bytes, const void* a, size_t na, const void* b,
+                        size_t nb, void* out, void* stream);
+gfb_status gfb_convolve_host(gfb_field* f, int elem_bytes, const void* a, size_t na, const void* b,
+                             size_t nb, void* out);
+/* C[batch][M][N] = A[batch][M][K] · B[batch or 1][K][N] over the field.  matmul_jit
+ * (_domains/_linalg.py:180-308).  b_batched = 0 broadcasts one B to every batch. */
+gfb_status gfb_matmul(gfb_field* f, int elem_bytes, const void* A, const void* B, void* C,
+                      size_t batch, size_t M, size_t K, size_t N, int b_batched, void* stream);
+gfb_status gfb_matmul_host(gfb_field* f, int elem_bytes, const void* A, const void* B, void* C,
+                           size_t batch, size_t M, size_t K, size_t N, int b_batched);
+
+/* ------------------------------------------------------------ Reed-Solomon ---- */
+/* Replaces ReedSolomon.__init__ (_codes/_reed_solomon.py:111-218) +
+ * _poly_to_generator_matrix (_codes/_cyclic.py:198-226, systematic) for codes over
+ * GF(2^m), m <= 8: generator roots alpha^c .. alpha^(c+d-2), d = n-k+1. */
+gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha);
+void gfb_rs_destroy(gfb_rs_code* rs);
+/* Copies of the code's constants (host memory, caller-allocated):
+ *   generator_poly: n-k+1 coefficients, degree-descending;  parity: k x (n-k) matrix P of G=[I|P]. */
+gfb_status gfb_rs_get_generator_poly(const gfb_rs_code* rs, uint8_t* generator_poly);
+gfb_status gfb_rs_get_parity_matrix(const gfb_rs_code* rs, uint8_t* parity);
+/* Systematic encode: msg [N][ks] → codeword [N][ks + (n-k)], ks <= k (shortened codes pad
+ * leading zeros).  _LinearCode._encode_message (_codes/_linear.py:270-284). */
+gfb_status gfb_rs_encode(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* codeword, size_t N,
+                         void* stream);
+/* Errors-and-erasures decode: received [N][ns] (+ optional erasure mask [N][ns], bytes 0/1, may
+ * be NULL) → corrected codewords [N][ns] and n_errors [N] (int64; -1 = uncorrectable, row left
+ * equal to the received row).  bch_decode_jit.implementation (_codes/_bch.py:1337-1578). */
+gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t* erasures, int ns,
+                         uint8_t* decoded, int64_t* n_errors, size_t N, void* stream);
+gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* codeword,
+                              size_t N);
+gfb_status gfb_rs_decode_host(gfb_rs_code* rs, const uint8_t* received, const uint8_t* erasures,
+                              int ns, uint8_t* decoded, int64_t* n_errors, size_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALOIS_B200_H */
