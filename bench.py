@@ -1,0 +1,602 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the galois_b200 hot path (driver contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gfp_mul|ntt|rs_decode|gf2_128_mul]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Default workload = BASELINE.json configs[1]: GF(2^31-1) element-wise multiply of two 1e8-element int64
+arrays ("uint64" in BASELINE.json; galois has no uint64 dtype).  One "step" = one pass of
+the multiply kernel over the whole 1e8-element batch resident in HBM.  `value` is field multiplications
+per second over all ranks; `e2e` is the same metric through the NumPy-facing FieldArray API
+(`x * y` on pinned host ndarrays: H2D + kernel + D2H inside the timed region).
+
+One JSON line on stdout (rank 0).  Multi-GPU: the element-wise arrays and NTT batches shard by rank with
+no data-path collective; timing is the max over ranks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+P_M31 = 2**31 - 1
+P_NTT = 998244353
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def measured_hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.load(open(f))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(kernel_key: str):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/*traffic*.json), or None."""
+    for f in sorted((ROOT / "profiles").glob("*traffic*.json"), reverse=True):
+        try:
+            d = json.load(open(f))
+            if kernel_key in d:
+                return d[kernel_key]
+        except Exception:
+            continue
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    import torch
+
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_steps(step_fn, steps: int, warmup: int, world: int):
+    """W untimed warm-ups, then EXACTLY `steps` steps between barrier+synchronize pairs; CUDA events on the
+    current torch stream (the stream every kernel here is launched on).  Returns max-over-ranks milliseconds."""
+    import torch
+
+    for _ in range(warmup):
+        step_fn()
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+class GfpMul:
+    """BASELINE configs[1]: GF(2^31-1) x*y, 1e8 int64 elements per GPU (weak scaling)."""
+
+    name = "GF(2^31-1) multiply, 1e8-element int64 arrays per GPU (BASELINE configs[1])"
+    metric, unit, dtype, scaling = "gfp_mul_per_sec", "field-mul/s", "int64", "weak"
+    kernel = "k_binary<u64, PrimeMersenne31, MUL>"
+    n = 10**8
+    bytes_per_unit = 24  # 2 x 8 B read + 8 B write
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+
+        self.gb, self.torch = gb, torch
+        self.GF = gb.GF(P_M31)
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        x = torch.randint(0, P_M31, (self.n,), dtype=torch.int64, device="cuda", generator=g)
+        y = torch.randint(1, P_M31, (self.n,), dtype=torch.int64, device="cuda", generator=g)
+        self.x = gb.DeviceArray(self.GF, x.view(torch.uint8), (self.n,), np.int64)
+        self.y = gb.DeviceArray(self.GF, y.view(torch.uint8), (self.n,), np.int64)
+        self.out = gb.DeviceArray.empty(self.GF, (self.n,), np.int64)
+        self.units_per_step = self.n
+        self.launches_per_step = 1
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        from galois_b200 import _lib
+
+        st = _lib.lib().gfb_binary(self.GF._handle(), _lib.GFB_MUL, 8, self.x.data_ptr, self.y.data_ptr,
+                                   self.out.data_ptr, self.n, self.gb.DeviceArray._stream())
+        _lib.check(st, "gfb_binary")
+
+    def check(self):
+        import oracle
+
+        idx = slice(0, 200_000)
+        xs = self.x.tensor.view(self.torch.int64)[idx].cpu().numpy()
+        ys = self.y.tensor.view(self.torch.int64)[idx].cpu().numpy()
+        got = self.out.tensor.view(self.torch.int64)[idx].cpu().numpy()
+        want = oracle.Field.prime(P_M31).mul(xs, ys)
+        assert np.array_equal(got, want), "GPU result differs from the oracle"
+
+    # end-to-end through the public API with host ndarrays
+    def e2e_setup(self):
+        self.hx = self.GF.Random(self.n, seed=1, dtype=np.int64)
+        self.hy = self.GF.Random(self.n, seed=2, low=1, dtype=np.int64)
+        self.h2d, self.d2h = 2 * 8 * self.n, 8 * self.n
+
+    def e2e_step(self):
+        self.hz = self.hx * self.hy
+
+    def cpu_step(self, threads):
+        import oracle
+
+        if not hasattr(self, "cx"):
+            rng = np.random.default_rng(1)
+            self.cx = rng.integers(0, P_M31, self.n, dtype=np.int64)
+            self.cy = rng.integers(1, P_M31, self.n, dtype=np.int64)
+            self.cz = np.empty_like(self.cx)
+        oracle.prime_mul_i64(P_M31, self.cx, self.cy, self.cz, threads=threads)
+        return self.n
+
+    cpu_sample = "full 1e8-element int64 arrays, (a*b) % p loop (_calculate.py:337-340) split over OpenMP threads"
+
+
+class Ntt:
+    """BASELINE configs[2]: 2^20-point NTT over GF(998244353), batch 4096 sharded over the ranks (strong)."""
+
+    metric, unit, dtype, scaling = "ntt_2p20_per_sec", "NTT/s", "uint32", "strong"
+    kernel = "k_ntt_pass1 + k_ntt_pass2"
+    N = 2**20
+    bytes_per_unit = 2 * 4 * 2**20  # 8 MiB per transform
+
+    def __init__(self, rank, world, batch=4096):
+        import torch
+
+        import galois_b200 as gb
+
+        self.gb, self.torch = gb, torch
+        self.GF = gb.GF(P_NTT)
+        self.batch_total = batch
+        self.rows = batch // world
+        self.name = f"NTT 2^20 over GF(998244353), batch {batch} sharded over {world} GPU(s) (BASELINE configs[2])"
+        g = torch.Generator(device="cuda").manual_seed(3 + rank)
+        x = torch.randint(0, P_NTT, (self.rows, self.N), dtype=torch.int32, device="cuda", generator=g)
+        self.x = gb.DeviceArray(self.GF, x.view(torch.uint8).reshape(-1), (self.rows, self.N), np.uint32)
+        self.out = gb.DeviceArray.empty(self.GF, (self.rows, self.N), np.uint32)
+        self.units_per_step = self.rows
+        self.launches_per_step = 2 * ((self.rows + 15) // 16)
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        self.gb.ntt_device(self.x, out=self.out)
+
+    def check(self):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        omega = int(self.GF.primitive_root_of_unity(self.N))
+        row = self.x.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        got = self.out.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, F.fft(row, omega)), "GPU NTT differs from the oracle"
+
+    def e2e_setup(self):
+        self.e2e_rows = min(self.rows, 256)
+        self.hx = self.GF.Random((self.e2e_rows, self.N), seed=3)
+        self.h2d = self.d2h = 4 * self.N * self.e2e_rows
+        self.e2e_units = self.e2e_rows
+
+    def e2e_step(self):
+        self.hz = self.gb.ntt(self.hx)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        rows = max(threads, 8)
+        if not hasattr(self, "cx"):
+            self.cx = np.random.default_rng(3).integers(0, P_NTT, (rows, self.N), dtype=np.int64)
+            self.omega = int(self.GF.primitive_root_of_unity(self.N))
+        F.fft(self.cx, self.omega, threads=threads)
+        return rows
+
+    cpu_sample = "max(threads, 8) rows of the 4096 (one 1-D fft_jit-style transform per row, rows over OpenMP threads)"
+
+
+class RsDecode:
+    """BASELINE configs[4]: RS(255,223) decode of codewords with 16 symbol errors each (t = 16)."""
+
+    metric, unit, dtype, scaling = "rs255_223_decode_cw_per_sec", "codeword/s", "u8", "strong"
+    kernel = "k_rs_decode"
+    bytes_per_unit = 518
+
+    def __init__(self, rank, world, total=10**6):
+        import torch
+
+        import galois_b200 as gb
+
+        self.gb, self.torch = gb, torch
+        self.rs = gb.ReedSolomon(255, 223)
+        self.N = total // world
+        self.name = f"RS(255,223) decode, {total} codewords x 16 errors sharded over {world} GPU(s) (BASELINE configs[4])"
+        GF = self.rs.field
+        M = GF.Random((self.N, 223), seed=6 + rank)
+        dC = self.rs.encode_device(M.to_device())
+        C = dC.tensor.view(self.N, 255)
+        g = torch.Generator(device="cuda").manual_seed(7 + rank)
+        # 16 distinct positions per row: top-16 of random keys
+        keys = torch.rand((self.N, 255), device="cuda", generator=g)
+        pos = keys.topk(16, dim=1).indices
+        err = torch.randint(1, 256, (self.N, 16), device="cuda", generator=g, dtype=torch.int32).to(torch.uint8)
+        R = C.clone()
+        R.scatter_(1, pos, R.gather(1, pos) ^ err)
+        self.C = C
+        self.R = gb.DeviceArray(GF, R.reshape(-1), (self.N, 255), np.uint8)
+        self.units_per_step = self.N
+        self.launches_per_step = 1
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        self.dec, self.nerr = self.rs.decode_device(self.R)
+
+    def check(self):
+        assert bool((self.nerr == 16).all()), "not every codeword reported 16 corrected errors"
+        assert bool((self.dec.tensor.view(self.N, 255) == self.C).all()), "decoded codewords differ from the originals"
+
+    def e2e_setup(self):
+        self.hR = self.R.cpu()
+        self.h2d, self.d2h = 255 * self.N, 255 * self.N + 8 * self.N
+        self.e2e_units = self.N
+
+    def e2e_step(self):
+        self.hz = self.rs.decode(self.hR, output="codeword", errors=True)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        n = 250 * threads
+        if not hasattr(self, "ors"):
+            self.ors = oracle.ReedSolomon(oracle.Field.binary(8, 0x11D, alpha=2), 255, 223)
+            self.cR = np.asarray(self.R.cpu())[:n].astype(np.int64)
+        self.ors.decode(self.cR, threads=threads)
+        return len(self.cR)
+
+    cpu_sample = "250 codewords per thread with 16 errors each (bch_decode_jit restatement, codewords over OpenMP threads)"
+
+
+class Gf128Mul:
+    """BASELINE configs[3]: GF(2^128) (GCM polynomial) multiply, 1e7 elements."""
+
+    name = "GF(2^128) x^128+x^7+x^2+x+1 multiply, 1e7 elements (BASELINE configs[3])"
+    metric, unit, dtype, scaling = "gf2_128_mul_per_sec", "field-mul/s", "u128", "weak"
+    kernel = "k_binary<u128, Binary128, MUL>"
+    n = 10**7
+    bytes_per_unit = 48
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+
+        self.gb, self.torch = gb, torch
+        self.GF = gb.GF(2**128, irreducible_poly="x^128 + x^7 + x^2 + x + 1", primitive_element=2, verify=False)
+        g = torch.Generator(device="cuda").manual_seed(5 + rank)
+        a = torch.randint(-(2**63), 2**63 - 1, (self.n, 2), dtype=torch.int64, device="cuda", generator=g)
+        b = torch.randint(-(2**63), 2**63 - 1, (self.n, 2), dtype=torch.int64, device="cuda", generator=g)
+        self.a = gb.DeviceArray(self.GF, a.view(torch.uint8).reshape(-1), (self.n,), np.object_)
+        self.b = gb.DeviceArray(self.GF, b.view(torch.uint8).reshape(-1), (self.n,), np.object_)
+        self.out = gb.DeviceArray.empty(self.GF, (self.n,), np.object_)
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = self.n, 1, 0, 0
+
+    def step(self):
+        from galois_b200 import _lib
+
+        st = _lib.lib().gfb_binary(self.GF._handle(), _lib.GFB_MUL, 16, self.a.data_ptr, self.b.data_ptr,
+                                   self.out.data_ptr, self.n, self.gb.DeviceArray._stream())
+        _lib.check(st, "gfb_binary")
+
+    def check(self):
+        import oracle
+
+        O = oracle.Field128(128, (1 << 128) | 0x87)
+        k = 20000
+        la = self.a.tensor[: 16 * k].cpu().numpy().view(np.uint64).reshape(-1, 2)
+        lb = self.b.tensor[: 16 * k].cpu().numpy().view(np.uint64).reshape(-1, 2)
+        got = self.out.tensor[: 16 * k].cpu().numpy().view(np.uint64).reshape(-1, 2)
+        assert np.array_equal(got, O.mul(la, lb, threads=8)), "GPU GF(2^128) product differs from the oracle"
+
+    def e2e_setup(self):
+        self.e2e_units = None
+
+    def cpu_step(self, threads):
+        import oracle
+
+        O = oracle.Field128(128, (1 << 128) | 0x87)
+        n = 200_000 * threads
+        if not hasattr(self, "ca"):
+            rng = np.random.default_rng(5)
+            self.ca = rng.integers(0, 2**64, (n, 2), dtype=np.uint64)
+            self.cb = rng.integers(0, 2**64, (n, 2), dtype=np.uint64)
+        O.mul(self.ca, self.cb, threads=threads)
+        return n
+
+    cpu_sample = "2e5 elements per thread, shift-and-xor multiply on 128-bit integers (the reference itself runs this field on Python ints)"
+
+
+WORKLOADS = {"gfp_mul": GfpMul, "ntt": Ntt, "rs_decode": RsDecode, "gf2_128_mul": Gf128Mul}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_threads() -> int:
+    import oracle
+
+    return max(1, min(oracle.max_threads(), os.cpu_count() or 1))
+
+
+def time_cpu(work, target_seconds=12.0, max_reps=50):
+    """Time `work.cpu_step` for roughly target_seconds; returns (units/s, reps, seconds, threads)."""
+    threads = cpu_threads()
+    work.cpu_step(threads)  # warm-up (allocations, page faults, OpenMP pool)
+    units, reps, t0 = 0, 0, time.perf_counter()
+    while reps < max_reps:
+        units += work.cpu_step(threads)
+        reps += 1
+        if time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return units / dt, reps, dt, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
+    Python + Numba and is not present on the GPU box), on every host thread it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cls = WORKLOADS[args.workload]
+    work = cls.__new__(cls)  # CPU leg only: no CUDA objects are created
+    if cls is Ntt:
+        import galois_b200 as gb
+
+        work.GF = gb.GF(P_NTT)  # host-side constants only (omega)
+    threads = cpu_threads()
+    if cls is RsDecode:
+        # the CPU leg needs received words: build them with the oracle itself
+        import oracle
+
+        F = oracle.Field.binary(8, 0x11D, alpha=2)
+        work.ors = oracle.ReedSolomon(F, 255, 223)
+        rng = np.random.default_rng(7)
+        n = 250 * threads
+        C = work.ors.encode(rng.integers(0, 256, (n, 223)), threads=threads)
+        for i in range(n):
+            pos = rng.choice(255, 16, replace=False)
+            C[i, pos] ^= rng.integers(1, 256, 16)
+        work.cR = C
+    for _ in range(max(args.warmup, 1)):
+        work.cpu_step(threads)
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(args.steps):
+        units += work.cpu_step(threads)
+    dt = time.perf_counter() - t0
+    value = units / dt
+    line = {
+        "impl": "reference", "metric": cls.metric, "value": value, "unit": cls.unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": cls.scaling, "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
+        "config": {"workload": getattr(cls, "name", cls.__doc__.strip().split("\n")[0].rstrip(".")),
+                   "note": "CPU oracle port of the reference path (oracle/gf_oracle.c); each step is a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": threads, "kind": "port", "sample": cls.cpu_sample},
+        "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gfp_mul", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads in the default run")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    rank, world, local = dist_setup(args.gpus)
+    cls = WORKLOADS[args.workload]
+    work = cls(rank, world)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = time_steps(work.step, args.steps, args.warmup, world)
+    clocks = sampler.stop() if rank == 0 else None
+    work.check()
+    workload_name = work.name
+    launches = args.steps * work.launches_per_step
+    per_gpu_units = work.units_per_step
+
+    total_units = work.units_per_step * world * args.steps
+    value = total_units / (ms / 1e3)
+    peak, peak_src = measured_hbm_peak()
+    # dominant kernel: algorithmic bytes of one step on this rank / mean device time of one step
+    achieved = work.units_per_step * cls.bytes_per_unit / (ms / 1e3 / args.steps) / 1e9
+
+    # ---- end to end through the public API with host buffers (same metric)
+    e2e = None
+    work.e2e_setup()
+    if getattr(work, "e2e_units", work.units_per_step) is not None:
+        e2e_units = getattr(work, "e2e_units", work.units_per_step)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            work.e2e_step()
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            work.e2e_step()
+        barrier_sync(world)
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / 1e3
+        e2e = {"value": e2e_units * world * e2e_steps / dt, "unit": cls.unit, "h2d_bytes_per_step": work.h2d,
+               "d2h_bytes_per_step": work.d2h, "steps": e2e_steps,
+               "api": "FieldArray ufunc / ntt / ReedSolomon.decode on pinned host ndarrays (gfb_*_host pipeline)"}
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only), bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, reps, secs, threads = time_cpu(work)
+        cpu = {"value": v, "unit": cls.unit, "cores": threads, "kind": "port",
+               "sample": f"{cls.cpu_sample}; {reps} repetitions in {secs:.1f} s"}
+
+    # ---- secondary workloads (default run only): short device-resident timings of the other BASELINE configs
+    extras = {}
+    if world == 1 and args.workload == "gfp_mul" and not args.no_extras:
+        del work
+        torch.cuda.empty_cache()
+        for key, ecls, kw in (("ntt", Ntt, {"batch": 512}), ("rs_decode", RsDecode, {"total": 10**6}),
+                              ("gf2_128_mul", Gf128Mul, {})):
+            try:
+                w = ecls(0, 1, **kw)
+                ems = time_steps(w.step, 5, 3, 1)
+                w.check()
+                extras[key] = {"metric": ecls.metric, "value": w.units_per_step * 5 / (ems / 1e3), "unit": ecls.unit,
+                               "workload": w.name, "ms_per_step": ems / 5,
+                               "hbm_gbs": w.units_per_step * ecls.bytes_per_unit / (ems / 5e3) / 1e9}
+                del w
+                torch.cuda.empty_cache()
+            except Exception as exc:  # a secondary workload must not take the headline down
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    line = {
+        "metric": cls.metric, "value": value, "unit": cls.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cls.scaling,
+        "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
+        "config": {"workload": workload_name, "parallelism": f"shard{world}",
+                   "l2": "inputs larger than L2 (no flush needed)", "units_per_gpu_per_step": per_gpu_units},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": recorded_traffic(args.workload), "kernel": cls.kernel, "peak_source": peak_src,
+                     "algorithmic_bytes_per_unit": cls.bytes_per_unit},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if extras:
+        line["extras"] = extras
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,7 +114,7 @@ gfb_status gfb_field_create(gfb_field** out, int kind, uint64_t order_lo, int de
         }
         if (degree <= 12)
             f->impl = gfb::IMPL_BIN_LUT;
-        else if (degree <= 64)
+        else if (degree <= 63)
             f->impl = gfb::IMPL_BIN_CALC;
         else
             f->impl = gfb::IMPL_BIN_128;

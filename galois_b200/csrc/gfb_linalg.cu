@@ -1,0 +1,271 @@
+// gfb_linalg.cu — polynomial convolution and matrix multiplication over GF(p) / GF(2^m).
+//
+// gfb_convolve replaces convolve_jit (/root/reference/src/galois/_domains/_function.py:111-167):
+//   c[k] = sum_i a[i] * b[k-i] in the field.  The reference has two code paths (integer np.convolve
+//   + one `% p` when it cannot overflow, schoolbook with ADD/MULTIPLY otherwise); both compute this
+//   same exact value, so one kernel serves both.
+// gfb_matmul replaces matmul_jit (_domains/_linalg.py:286-308) and, for prime fields, the float-BLAS
+//   detour `_lapack_linalg` (_linalg.py:21-75) — again the same exact field result.
+//
+// These are integer kernels; the GF(p) inner products accumulate unreduced 64-bit products in a
+// 128-bit accumulator and reduce once per output.  No tensor cores (exact integer work).
+#include "gfb_common.cuh"
+
+namespace gfb {
+
+// ----------------------------------------------------------------------------------------
+// dot-product accumulators: lazy for prime fields, xor for binary fields
+// ----------------------------------------------------------------------------------------
+template <typename F>
+struct DotAcc {
+    typename F::elem acc;
+    __device__ __forceinline__ void init(const F& f) { acc = f.zero(); }
+    __device__ __forceinline__ void fma(const F& f, typename F::elem a, typename F::elem b) { acc = f.add(acc, f.mul(a, b)); }
+    __device__ __forceinline__ typename F::elem done(const F&) { return acc; }
+};
+
+template <>
+struct DotAcc<PrimeBarrett> {
+    unsigned long long lo, hi;
+    __device__ __forceinline__ void init(const PrimeBarrett&) { lo = hi = 0ull; }
+    __device__ __forceinline__ void fma(const PrimeBarrett&, uint32_t a, uint32_t b) {
+        unsigned long long x = (unsigned long long)a * b;
+        lo += x;
+        hi += (lo < x) ? 1ull : 0ull;
+    }
+    __device__ __forceinline__ uint32_t done(const PrimeBarrett& f) {
+        // (hi * 2^64 + lo) mod p, hi < 2^32
+        uint32_t r64 = f.reduce64(0xFFFFFFFFFFFFFFFFull);  // (2^64 - 1) mod p
+        r64 = f.add(r64, 1u % f.p);                        // 2^64 mod p
+        uint32_t h = f.reduce64(hi);
+        uint32_t l = f.reduce64(lo);
+        return f.add(f.mul(h, r64), l);
+    }
+};
+
+template <>
+struct DotAcc<PrimeMersenne31> {
+    unsigned long long lo, hi;
+    __device__ __forceinline__ void init(const PrimeMersenne31&) { lo = hi = 0ull; }
+    __device__ __forceinline__ void fma(const PrimeMersenne31&, uint32_t a, uint32_t b) {
+        unsigned long long x = (unsigned long long)a * b;
+        lo += x;
+        hi += (lo < x) ? 1ull : 0ull;
+    }
+    __device__ __forceinline__ uint32_t done(const PrimeMersenne31& f) {
+        // 2^64 = 2^(31*2+2) ≡ 4 (mod 2^31-1)
+        const unsigned long long p = PrimeMersenne31::p;
+        unsigned long long l = (lo & p) + ((lo >> 31) & p) + (lo >> 62);  // < 3 * 2^31
+        unsigned long long h = (hi % p) * 4ull;                           // hi < 2^32
+        unsigned long long s = (l + h) % p;
+        return (uint32_t)s;
+    }
+};
+
+// ----------------------------------------------------------------------------------------
+// convolution: one thread per output coefficient, operands staged through shared memory tiles
+// ----------------------------------------------------------------------------------------
+constexpr int kConvThreads = 256;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kConvThreads) k_convolve(F f, const T* __restrict__ a, size_t na,
+                                                            const T* __restrict__ b, size_t nb, T* __restrict__ out) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    const size_t nc = na + nb - 1;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    // i ranges over max(0, k-nb+1) .. min(k, na-1)
+    const size_t i0 = k >= nb - 1 ? k - (nb - 1) : 0;
+    const size_t i1 = k < na - 1 ? k : na - 1;
+    DotAcc<F> acc;
+    acc.init(f);
+    for (size_t i = i0; i <= i1; ++i) acc.fma(f, to_elem<E, T>(a[i]), to_elem<E, T>(b[k - i]));
+    out[k] = to_store<T, E>(acc.done(f));
+}
+
+// ----------------------------------------------------------------------------------------
+// matmul: 16x16 output tile per block, K swept in tiles of 16 through shared memory
+// ----------------------------------------------------------------------------------------
+constexpr int kTile = 16;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kTile* kTile) k_matmul(F f, const T* __restrict__ A, const T* __restrict__ B,
+                                                          T* __restrict__ C, size_t M, size_t K, size_t N, int b_batched,
+                                                          size_t smem_field_bytes) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    E* sA = reinterpret_cast<E*>(reinterpret_cast<char*>(smem_raw) + smem_field_bytes);
+    E* sB = sA + kTile * (kTile + 1);
+    const size_t batch = blockIdx.z;
+    const T* Ab = A + batch * M * K;
+    const T* Bb = B + (b_batched ? batch * K * N : 0);
+    T* Cb = C + batch * M * N;
+    const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;
+    const size_t row = (size_t)blockIdx.y * kTile + ty;
+    const size_t col = (size_t)blockIdx.x * kTile + tx;
+    DotAcc<F> acc;
+    acc.init(f);
+    for (size_t k0 = 0; k0 < K; k0 += kTile) {
+        sA[ty * (kTile + 1) + tx] = (row < M && k0 + tx < K) ? to_elem<E, T>(Ab[row * K + k0 + tx]) : f.zero();
+        sB[ty * (kTile + 1) + tx] = (k0 + ty < K && col < N) ? to_elem<E, T>(Bb[(k0 + ty) * N + col]) : f.zero();
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kTile; ++kk) acc.fma(f, sA[ty * (kTile + 1) + kk], sB[kk * (kTile + 1) + tx]);
+        __syncthreads();
+    }
+    if (row < M && col < N) Cb[row * N + col] = to_store<T, E>(acc.done(f));
+}
+
+template <typename F>
+static size_t smem_for(const F& f) {
+    if constexpr (F::kNeedsSmem)
+        return (f.smem_bytes() + 15) & ~(size_t)15;
+    else
+        return 0;
+}
+
+template <typename T, typename F>
+static gfb_status launch_convolve(F f, const void* a, size_t na, const void* b, size_t nb, void* out, cudaStream_t st) {
+    const size_t nc = na + nb - 1;
+    const unsigned grid = (unsigned)((nc + kConvThreads - 1) / kConvThreads);
+    k_convolve<T, F><<<grid, kConvThreads, smem_for(f), st>>>(f, (const T*)a, na, (const T*)b, nb, (T*)out);
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+template <typename T, typename F>
+static gfb_status launch_matmul(F f, const void* A, const void* B, void* C, size_t batch, size_t M, size_t K, size_t N,
+                                int b_batched, cudaStream_t st) {
+    using E = typename F::elem;
+    const size_t fs = smem_for(f);
+    const size_t smem = fs + 2 * kTile * (kTile + 1) * sizeof(E);
+    dim3 grid((unsigned)((N + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile), (unsigned)batch);
+    if (batch > 65535 || grid.y > 65535) return GFB_ERR_UNSUPPORTED;
+    k_matmul<T, F><<<grid, kTile * kTile, smem, st>>>(f, (const T*)A, (const T*)B, (T*)C, M, K, N, b_batched, fs);
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+template <typename F>
+static gfb_status conv_by_width(F f, int eb, const void* a, size_t na, const void* b, size_t nb, void* out,
+                                cudaStream_t st) {
+    switch (eb) {
+        case 1: return launch_convolve<uint8_t, F>(f, a, na, b, nb, out, st);
+        case 2: return launch_convolve<uint16_t, F>(f, a, na, b, nb, out, st);
+        case 4: return launch_convolve<uint32_t, F>(f, a, na, b, nb, out, st);
+        case 8: return launch_convolve<unsigned long long, F>(f, a, na, b, nb, out, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
+template <typename F>
+static gfb_status matmul_by_width(F f, int eb, const void* A, const void* B, void* C, size_t batch, size_t M, size_t K,
+                                  size_t N, int bb, cudaStream_t st) {
+    switch (eb) {
+        case 1: return launch_matmul<uint8_t, F>(f, A, B, C, batch, M, K, N, bb, st);
+        case 2: return launch_matmul<uint16_t, F>(f, A, B, C, batch, M, K, N, bb, st);
+        case 4: return launch_matmul<uint32_t, F>(f, A, B, C, batch, M, K, N, bb, st);
+        case 8: return launch_matmul<unsigned long long, F>(f, A, B, C, batch, M, K, N, bb, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
+static bool width_ok(const gfb_field* f, int eb) {
+    if (f->impl == IMPL_BIN_128) return eb == 16;
+    if (eb != 1 && eb != 2 && eb != 4 && eb != 8) return false;
+    if (eb == 8) return true;
+    if (f->kind == GFB_PRIME) return (f->order_lo - 1) < (1ull << (8 * eb));
+    return f->degree <= 8 * eb;
+}
+
+}  // namespace gfb
+
+extern "C" {
+
+gfb_status gfb_convolve(gfb_field* f, int eb, const void* a, size_t na, const void* b, size_t nb, void* out,
+                        void* stream) {
+    using namespace gfb;
+    if (!f || !a || !b || !out || na == 0 || nb == 0) return GFB_ERR_BAD_ARG;
+    if (!width_ok(f, eb)) return GFB_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (f->impl) {
+        case IMPL_PRIME_M31: return conv_by_width(f->prime_m31(), eb, a, na, b, nb, out, st);
+        case IMPL_PRIME_BARRETT: return conv_by_width(f->prime_barrett(), eb, a, na, b, nb, out, st);
+        case IMPL_BIN_LUT: return conv_by_width(f->bin_lut(), eb, a, na, b, nb, out, st);
+        case IMPL_BIN_CALC: return conv_by_width(f->bin_calc(), eb, a, na, b, nb, out, st);
+        case IMPL_BIN_128: return launch_convolve<u128, Binary128>(f->bin_128(), a, na, b, nb, out, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
+gfb_status gfb_matmul(gfb_field* f, int eb, const void* A, const void* B, void* C, size_t batch, size_t M, size_t K,
+                      size_t N, int b_batched, void* stream) {
+    using namespace gfb;
+    if (!f || !A || !B || !C) return GFB_ERR_BAD_ARG;
+    if (batch == 0 || M == 0 || N == 0) return GFB_OK;
+    if (!width_ok(f, eb)) return GFB_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (f->impl) {
+        case IMPL_PRIME_M31: return matmul_by_width(f->prime_m31(), eb, A, B, C, batch, M, K, N, b_batched, st);
+        case IMPL_PRIME_BARRETT: return matmul_by_width(f->prime_barrett(), eb, A, B, C, batch, M, K, N, b_batched, st);
+        case IMPL_BIN_LUT: return matmul_by_width(f->bin_lut(), eb, A, B, C, batch, M, K, N, b_batched, st);
+        case IMPL_BIN_CALC: return matmul_by_width(f->bin_calc(), eb, A, B, C, batch, M, K, N, b_batched, st);
+        case IMPL_BIN_128: return launch_matmul<u128, Binary128>(f->bin_128(), A, B, C, batch, M, K, N, b_batched, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
+// host variants: one-shot copies (these operands are small next to the element-wise arrays)
+gfb_status gfb_convolve_host(gfb_field* f, int eb, const void* a, size_t na, const void* b, size_t nb, void* out) {
+    if (!f || !a || !b || !out || na == 0 || nb == 0) return GFB_ERR_BAD_ARG;
+    const size_t nc = na + nb - 1;
+    char* d = nullptr;
+    GFB_CUDA_TRY(cudaMalloc((void**)&d, (na + nb + nc) * (size_t)eb + 64));
+    char* da = d;
+    char* db = da + ((na * eb + 15) & ~(size_t)15);
+    char* dc = db + ((nb * eb + 15) & ~(size_t)15);
+    gfb_status st = GFB_OK;
+    cudaError_t e = cudaMemcpy(da, a, na * eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, nb * eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        st = gfb_convolve(f, eb, da, na, db, nb, dc, nullptr);
+        if (st == GFB_OK) e = cudaMemcpy(out, dc, nc * eb, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        gfb::set_last_error("gfb_convolve_host", e);
+        return GFB_ERR_CUDA;
+    }
+    return st;
+}
+
+gfb_status gfb_matmul_host(gfb_field* f, int eb, const void* A, const void* B, void* C, size_t batch, size_t M, size_t K,
+                           size_t N, int b_batched) {
+    if (!f || !A || !B || !C) return GFB_ERR_BAD_ARG;
+    if (batch == 0 || M == 0 || N == 0) return GFB_OK;
+    const size_t ba = batch * M * K * eb, bb = (b_batched ? batch : 1) * K * N * eb, bc = batch * M * N * eb;
+    char *da = nullptr, *db = nullptr, *dc = nullptr;
+    GFB_CUDA_TRY(cudaMalloc((void**)&da, ba + 16));
+    cudaError_t e = cudaMalloc((void**)&db, bb + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, bc + 16);
+    gfb_status st = GFB_OK;
+    if (e == cudaSuccess) e = cudaMemcpy(da, A, ba, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, B, bb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        st = gfb_matmul(f, eb, da, db, dc, batch, M, K, N, b_batched, nullptr);
+        if (st == GFB_OK) e = cudaMemcpy(C, dc, bc, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dc);
+    if (e != cudaSuccess) {
+        gfb::set_last_error("gfb_matmul_host", e);
+        return GFB_ERR_CUDA;
+    }
+    return st;
+}
+
+}  // extern "C"

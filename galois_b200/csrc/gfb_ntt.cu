@@ -1,0 +1,538 @@
+// gfb_ntt.cu — batched radix-2 NTT / INTT over prime fields for sm_100a.
+//
+// Replaces fft_jit / ifft_jit (/root/reference/src/galois/_domains/_function.py:170-392; radix-2
+// butterfly :337-352) behind galois.ntt / galois.intt (_ntt.py:239-278).  The reference computes
+//     X_k = sum_j x_j * omega^(j k)  (mod p),   natural order in and out,
+// one 1-D vector per call.  Any exact algorithm yields the same X; only omega (chosen by the caller
+// exactly as the reference does) and the optional 1/N scale matter for bit-exactness.
+//
+// Two device paths:
+//  * four-step fast path, N = 2^20 = 1024 x 1024, p < 2^31 (the BASELINE.json config):
+//      pass 1  : tile of 16 columns x 1024 rows → shared memory (transposed), one warp per column
+//                runs a 1024-point NTT as two in-register radix-32 rounds with a shared-memory
+//                exchange, multiplies by the four-step twiddle omega^(c*k) (x scale) and writes the
+//                tile back in place-layout to a uint32 workspace.
+//      pass 2  : tile of 16 rows x 1024 → shared memory, same warp NTT, transposed store
+//                X[k1 + 1024*k2].
+//    Butterflies are Harvey lazy butterflies with Shoup twiddles (values in [0,4p) when p < 2^30).
+//    Work is issued in chunks of kChunk transforms so that the workspace (64 MiB) stays L2-resident
+//    between the two passes: HBM traffic approaches the compulsory 8 B/element (4-byte storage).
+//  * generic path, any N = 2^k <= 2^24, any p < 2^32: one Stockham autosort radix-2 stage per
+//    launch, ping-ponging between two workspaces (mirrors the reference's own stage structure).
+//
+// Algorithmic bytes per transform: 2 * N * elem_bytes (read x once, write X once).
+#include <cstdlib>
+#include <cstring>
+
+#include "gfb_common.cuh"
+#include "gfb_host.cuh"
+
+struct gfb_ntt_plan {
+    gfb_field* field;
+    size_t n;
+    int log_n;
+    uint32_t p;
+    uint32_t omega, scale;
+    bool fast;             // four-step 1024 x 1024 path available
+    bool lazy;             // p < 2^30
+    // generic path
+    uint32_t* d_pow;       // omega^e, e < max(n/2, 1)
+    // fast path
+    uint2* d_tw4;          // [k*1024 + c] = (scale * omega^(c k), shoup)
+    uint2* d_zt;           // [k1*32 + t] = (zeta^(t k1), shoup), zeta = omega^1024
+    uint32_t rho[16], rho_sh[16];  // rho^e, rho = zeta^32 (primitive 32nd root), with Shoup companions
+};
+
+namespace gfb {
+
+constexpr int kNttChunk = 16;              // transforms per pass-1/pass-2 launch pair (64 MiB workspace)
+constexpr size_t kGenericWsBytes = (size_t)64 << 20;
+
+// ------------------------------------------------------------------------------------------------
+// table construction
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t shoup(uint32_t w, uint32_t p) {
+    return (uint32_t)((((unsigned long long)w) << 32) / p);
+}
+
+__global__ void k_build_pow(PrimeBarrett f, uint32_t omega, uint32_t* out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = f.pow_u64(omega, i);
+}
+
+// tw4[k*1024 + c] = scale * omega^(c*k)
+__global__ void k_build_tw4(PrimeBarrett f, uint32_t omega, uint32_t scale, uint2* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << 20)) return;
+    unsigned long long k = i >> 10, c = i & 1023;
+    uint32_t w = f.mul(f.pow_u64(omega, k * c), scale);
+    out[i] = make_uint2(w, shoup(w, f.p));
+}
+
+// zt[k1*32 + t] = zeta^(t*k1)
+__global__ void k_build_zt(PrimeBarrett f, uint32_t zeta, uint2* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 1024) return;
+    unsigned long long k1 = i >> 5, t = i & 31;
+    uint32_t w = f.pow_u64(zeta, k1 * t);
+    out[i] = make_uint2(w, shoup(w, f.p));
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path: one Stockham radix-2 stage per launch (structure of _function.py:337-352)
+//   in_view[k, qi, b] = in[(k*q + qi)*m + b],  out_view[qi, f, b] = out[(qi*2 + f)*m + b],
+//   twiddle(b) = omega^(q*b)
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_stockham_stage(PrimeBarrett f, const TI* __restrict__ in, TO* __restrict__ out,
+                                                         const uint32_t* __restrict__ pow, size_t n, size_t m, size_t batch,
+                                                         uint32_t scale) {
+    const size_t half = n >> 1;
+    const size_t total = half * batch;
+    const size_t q = half / m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = idx / half;
+        const size_t j = idx - row * half;  // j = qi*m + b
+        const size_t qi = j / m, b = j - qi * m;
+        const TI* src = in + row * n;
+        TO* dst = out + row * n;
+        uint32_t x0 = (uint32_t)src[qi * m + b];
+        uint32_t x1 = f.mul((uint32_t)src[(q + qi) * m + b], pow[q * b]);
+        uint32_t y0 = f.add(x0, x1), y1 = f.sub(x0, x1);
+        if (scale != 1u) {
+            y0 = f.mul(y0, scale);
+            y1 = f.mul(y1, scale);
+        }
+        dst[(qi * 2) * m + b] = (TO)y0;
+        dst[(qi * 2 + 1) * m + b] = (TO)y1;
+    }
+}
+
+template <typename T>
+__global__ void k_scale_copy(PrimeBarrett f, const T* in, T* out, size_t count, uint32_t scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (T)f.mul((uint32_t)in[i], scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path arithmetic
+// ------------------------------------------------------------------------------------------------
+struct Radix32Roots {
+    uint32_t w[16];
+    uint32_t ws[16];
+};
+
+template <bool LAZY>
+struct Mod {
+    uint32_t p, p2;
+    // conditional subtract without a compare: for x in [0, 2m), min(x, x - m) (the difference wraps when x < m)
+    static __device__ __forceinline__ uint32_t csub(uint32_t x, uint32_t m) { return min(x, x - m); }
+    // x * w mod p with Shoup companion ws = floor(w 2^32 / p); any 32-bit x.  LAZY: result in [0, 2p).
+    __device__ __forceinline__ uint32_t mul(uint32_t x, uint32_t w, uint32_t ws) const {
+        uint32_t q = __umulhi(x, ws);
+        uint32_t r = x * w - q * p;
+        if constexpr (!LAZY) r = csub(r, p);
+        return r;
+    }
+    // DIT butterfly (a, b) <- (a + t, a - t), t = b*w.  LAZY: in/out in [0, 4p); else in/out in [0, p).
+    __device__ __forceinline__ void bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) const {
+        if constexpr (LAZY) {
+            const uint32_t x = csub(a, p2);
+            const uint32_t t = mul(b, w, ws);
+            a = x + t;
+            b = x - t + p2;
+        } else {
+            const uint32_t t = mul(b, w, ws);
+            const uint32_t s = csub(a + t, p);
+            const uint32_t d = a - t;
+            b = min(d, d + p);  // a < t: d wrapped, d + p is the residue
+            a = s;
+        }
+    }
+    // butterfly with unit twiddle
+    __device__ __forceinline__ void bfly1(uint32_t& a, uint32_t& b) const {
+        if constexpr (LAZY) {
+            const uint32_t x = csub(a, p2), t = csub(b, p2);
+            a = x + t;
+            b = x - t + p2;
+        } else {
+            const uint32_t s = csub(a + b, p);
+            const uint32_t d = a - b;
+            b = min(d, d + p);
+            a = s;
+        }
+    }
+    // bring a lazy value into [0, p)
+    __device__ __forceinline__ uint32_t canon(uint32_t x) const {
+        if constexpr (LAZY) x = csub(x, p2);
+        return csub(x, p);
+    }
+};
+
+__host__ __device__ constexpr int brev5(int i) {
+    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// In-register 32-point DIT NTT.  On entry v[brev5(i)] = x[i]; on exit v[k] = sum_i x[i] rho^(i k).
+template <bool LAZY, int S>
+__device__ __forceinline__ void radix32_stage(uint32_t (&v)[32], const Mod<LAZY>& md, const Radix32Roots& rt) {
+    constexpr int half = 1 << S;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {  // the 16 butterflies of stage S, flat so that every index is static
+        const int j = g & (half - 1);
+        const int k = (g >> S) << (S + 1);
+        const int e = j * (16 >> S);  // twiddle rho^(j * 32 / (2*half))
+        if (e == 0)
+            md.bfly1(v[k + j], v[k + j + half]);
+        else
+            md.bfly(v[k + j], v[k + j + half], rt.w[e], rt.ws[e]);
+    }
+}
+
+template <bool LAZY>
+__device__ __forceinline__ void radix32(uint32_t (&v)[32], const Mod<LAZY>& md, const Radix32Roots& rt) {
+    radix32_stage<LAZY, 0>(v, md, rt);
+    radix32_stage<LAZY, 1>(v, md, rt);
+    radix32_stage<LAZY, 2>(v, md, rt);
+    radix32_stage<LAZY, 3>(v, md, rt);
+    radix32_stage<LAZY, 4>(v, md, rt);
+}
+
+constexpr int kRowStride = 1058;  // uint32 words per shared-memory row (1024 + 32 pad + 2: see file header)
+__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+
+// 1024-point NTT of one shared-memory row by one warp: X[k] left in natural order at row[padi(k)].
+// Values on exit are in [0, 4p) (LAZY) or [0, p).
+template <bool LAZY>
+__device__ __forceinline__ void warp_ntt1024(uint32_t* row, const Mod<LAZY>& md, const Radix32Roots& rt,
+                                             const uint2* __restrict__ zt) {
+    const int t = threadIdx.x & 31;
+    uint32_t v[32];
+    // round A: i = 32*i1 + i0, i0 = t; 32-point NTT over i1; then twiddle zeta^(i0*k1)
+#pragma unroll
+    for (int a = 0; a < 32; ++a) v[brev5(a)] = row[t + 33 * a];
+    radix32<LAZY>(v, md, rt);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        if (k1 == 0) {
+            row[t] = v[0];
+        } else {
+            const uint2 z = __ldg(&zt[k1 * 32 + t]);
+            row[t + 33 * k1] = md.mul(v[k1], z.x, z.y);
+        }
+    }
+    __syncwarp();
+    // round B: k1 = t; 32-point NTT over i0 (contiguous rows 32*k1 + i0); output k = k1 + 32*k0
+#pragma unroll
+    for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
+    __syncwarp();
+    radix32<LAZY>(v, md, rt);
+#pragma unroll
+    for (int k0 = 0; k0 < 32; ++k0) row[t + 33 * k0] = v[k0];
+    __syncwarp();
+}
+
+constexpr int kFastThreads = 256;
+constexpr int kTileW = 16;
+constexpr size_t kFastSmem = (size_t)kTileW * kRowStride * sizeof(uint32_t);
+
+// pass 1: column NTTs + four-step twiddle.  One CTA per (transform, 16-column tile).
+template <typename T, bool LAZY, int OCC>
+__global__ void __launch_bounds__(kFastThreads, OCC)
+    k_ntt_pass1(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint2* __restrict__ tw4,
+                const T* __restrict__ x, uint32_t* __restrict__ ws) {
+    extern __shared__ uint32_t tile[];
+    const size_t transform = blockIdx.x >> 6;
+    const int c0 = (blockIdx.x & 63) * kTileW;
+    const T* src = x + (transform << 20) + c0;
+    uint32_t* dst = ws + (transform << 20) + c0;
+#pragma unroll 8
+    for (int it = 0; it < 64; ++it) {
+        const int e = it * kFastThreads + threadIdx.x;
+        const int w = e & 15, r = e >> 4;
+        tile[w * kRowStride + padi(r)] = (uint32_t)src[(size_t)r * 1024 + w];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    warp_ntt1024<LAZY>(tile + (warp * 2) * kRowStride, md, rt, zt);
+    warp_ntt1024<LAZY>(tile + (warp * 2 + 1) * kRowStride, md, rt, zt);
+    __syncthreads();
+#pragma unroll 8
+    for (int it = 0; it < 64; ++it) {
+        const int e = it * kFastThreads + threadIdx.x;
+        const int w = e & 15, k = e >> 4;
+        const uint2 tw = __ldg(&tw4[(size_t)k * 1024 + c0 + w]);
+        uint32_t val = md.mul(tile[w * kRowStride + padi(k)], tw.x, tw.y);
+        if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
+        dst[(size_t)k * 1024 + w] = val;
+    }
+}
+
+// pass 2: row NTTs + transposed store.  One CTA per (transform, 16-row tile).
+template <typename T, bool LAZY, int OCC>
+__global__ void __launch_bounds__(kFastThreads, OCC)
+    k_ntt_pass2(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint32_t* __restrict__ ws,
+                T* __restrict__ y) {
+    extern __shared__ uint32_t tile[];
+    const size_t transform = blockIdx.x >> 6;
+    const int k1_0 = (blockIdx.x & 63) * kTileW;
+    const uint32_t* src = ws + (transform << 20) + (size_t)k1_0 * 1024;
+    T* dst = y + (transform << 20) + k1_0;
+#pragma unroll 8
+    for (int it = 0; it < 64; ++it) {
+        const int e = it * kFastThreads + threadIdx.x;
+        const int i = e & 1023, w = e >> 10;
+        tile[w * kRowStride + padi(i)] = src[(size_t)w * 1024 + i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    warp_ntt1024<LAZY>(tile + (warp * 2) * kRowStride, md, rt, zt);
+    warp_ntt1024<LAZY>(tile + (warp * 2 + 1) * kRowStride, md, rt, zt);
+    __syncthreads();
+#pragma unroll 8
+    for (int it = 0; it < 64; ++it) {
+        const int e = it * kFastThreads + threadIdx.x;
+        const int w = e & 15, k2 = e >> 4;
+        dst[(size_t)k2 * 1024 + w] = (T)md.canon(tile[w * kRowStride + padi(k2)]);
+    }
+}
+
+// Resident CTAs per SM for the fast-path kernels: 3 caps registers at 80 (a few spills), 2 leaves 128.
+// GFB_NTT_OCC=2|3 overrides the default for tuning runs.
+static int ntt_occupancy() {
+    static int occ = 0;
+    if (occ == 0) {
+        const char* e = getenv("GFB_NTT_OCC");
+        occ = (e && e[0] == '2') ? 2 : 3;
+    }
+    return occ;
+}
+
+template <typename T, bool LAZY, int OCC>
+static gfb_status run_fast_occ(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    Mod<LAZY> md{pl->p, pl->p * 2u};
+    Radix32Roots rt;
+    memcpy(rt.w, pl->rho, sizeof(rt.w));
+    memcpy(rt.ws, pl->rho_sh, sizeof(rt.ws));
+    static bool attr_set = false;
+    if (!attr_set) {
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kFastSmem));
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kFastSmem));
+        attr_set = true;
+    }
+    for (size_t off = 0; off < batch; off += kNttChunk) {
+        const size_t cnt = batch - off < (size_t)kNttChunk ? batch - off : (size_t)kNttChunk;
+        const unsigned grid = (unsigned)(cnt * 64);
+        k_ntt_pass1<T, LAZY, OCC>
+            <<<grid, kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, pl->d_tw4, x + (off << 20), ws);
+        k_ntt_pass2<T, LAZY, OCC><<<grid, kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, ws, y + (off << 20));
+    }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+template <typename T, bool LAZY>
+static gfb_status run_fast_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    return ntt_occupancy() == 2 ? run_fast_occ<T, LAZY, 2>(pl, x, y, batch, ws, st)
+                                : run_fast_occ<T, LAZY, 3>(pl, x, y, batch, ws, st);
+}
+
+template <typename T>
+static gfb_status run_generic_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, void* workspace, cudaStream_t st) {
+    PrimeBarrett f = pl->field->prime_barrett();
+    const size_t n = pl->n;
+    if (n == 1) {
+        const size_t cnt = batch;
+        k_scale_copy<T><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(f, x, y, cnt, pl->scale);
+        GFB_CUDA_TRY(cudaGetLastError());
+        return GFB_OK;
+    }
+    const size_t rows_per_chunk = kGenericWsBytes / (n * sizeof(uint32_t)) ? kGenericWsBytes / (n * sizeof(uint32_t)) : 1;
+    uint32_t* A = (uint32_t*)workspace;
+    uint32_t* B = A + rows_per_chunk * n;
+    const int S = pl->log_n;
+    for (size_t off = 0; off < batch; off += rows_per_chunk) {
+        const size_t cnt = batch - off < rows_per_chunk ? batch - off : rows_per_chunk;
+        const size_t total = (n >> 1) * cnt;
+        size_t blocks = (total + 255) / 256;
+        const size_t cap = (size_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        const unsigned grid = (unsigned)blocks;
+        const T* xin = x + off * n;
+        T* yout = y + off * n;
+        size_t m = 1;
+        for (int s = 0; s < S; ++s, m <<= 1) {
+            const bool first = s == 0, last = s == S - 1;
+            const uint32_t sc = last ? pl->scale : 1u;
+            uint32_t* src_ws = (s & 1) ? A : B;  // stage s reads what stage s-1 wrote
+            uint32_t* dst_ws = (s & 1) ? B : A;
+            if (first && last)
+                k_stockham_stage<T, T><<<grid, 256, 0, st>>>(f, xin, yout, pl->d_pow, n, m, cnt, sc);
+            else if (first)
+                k_stockham_stage<T, uint32_t><<<grid, 256, 0, st>>>(f, xin, dst_ws, pl->d_pow, n, m, cnt, sc);
+            else if (last)
+                k_stockham_stage<uint32_t, T><<<grid, 256, 0, st>>>(f, src_ws, yout, pl->d_pow, n, m, cnt, sc);
+            else
+                k_stockham_stage<uint32_t, uint32_t><<<grid, 256, 0, st>>>(f, src_ws, dst_ws, pl->d_pow, n, m, cnt, sc);
+        }
+    }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+static uint32_t host_powmod(uint32_t b, unsigned long long e, uint32_t p) {
+    unsigned long long r = 1 % p, x = b % p;
+    while (e) {
+        if (e & 1) r = r * x % p;  // p < 2^32: products fit 64 bits
+        x = x * x % p;
+        e >>= 1;
+    }
+    return (uint32_t)r;
+}
+
+}  // namespace gfb
+
+extern "C" {
+
+gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint64_t omega, uint64_t scale) {
+    using namespace gfb;
+    if (!out) return GFB_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!f || f->kind != GFB_PRIME) return GFB_ERR_BAD_ARG;
+    if (n == 0 || (n & (n - 1)) != 0) return GFB_ERR_UNSUPPORTED;  // mixed radix: SURVEY.md §8f.3
+    if (n > ((size_t)1 << 24)) return GFB_ERR_UNSUPPORTED;
+    const uint32_t p = f->p;
+    if (omega >= p || scale >= p || scale == 0) return GFB_ERR_BAD_ARG;
+    if (((unsigned long long)p - 1ull) % n != 0) return GFB_ERR_BAD_ARG;
+    // omega must be a primitive n-th root of unity
+    if (host_powmod((uint32_t)omega, n, p) != 1u % p) return GFB_ERR_BAD_ARG;
+    if (n > 1 && host_powmod((uint32_t)omega, n / 2, p) == 1u) return GFB_ERR_BAD_ARG;
+
+    gfb_ntt_plan* pl = (gfb_ntt_plan*)calloc(1, sizeof(gfb_ntt_plan));
+    pl->field = f;
+    pl->n = n;
+    pl->log_n = 0;
+    while (((size_t)1 << pl->log_n) < n) pl->log_n++;
+    pl->p = p;
+    pl->omega = (uint32_t)omega;
+    pl->scale = (uint32_t)scale;
+    pl->fast = (n == ((size_t)1 << 20)) && p < (1u << 31);
+    pl->lazy = p < (1u << 30);
+    PrimeBarrett fb = f->prime_barrett();
+    const size_t npow = n / 2 ? n / 2 : 1;
+    cudaError_t e = cudaSuccess;
+    if (!pl->fast) {
+        e = cudaMalloc((void**)&pl->d_pow, npow * sizeof(uint32_t));
+        if (e == cudaSuccess) {
+            k_build_pow<<<(unsigned)((npow + 255) / 256), 256>>>(fb, pl->omega, pl->d_pow, npow);
+            e = cudaGetLastError();
+        }
+    } else {
+        const uint32_t zeta = host_powmod(pl->omega, 1024, p);
+        const uint32_t rho = host_powmod(zeta, 32, p);
+        for (int i = 0; i < 16; ++i) {
+            pl->rho[i] = host_powmod(rho, i, p);
+            pl->rho_sh[i] = (uint32_t)((((unsigned long long)pl->rho[i]) << 32) / p);
+        }
+        e = cudaMalloc((void**)&pl->d_tw4, ((size_t)1 << 20) * sizeof(uint2));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt, 1024 * sizeof(uint2));
+        if (e == cudaSuccess) {
+            k_build_tw4<<<4096, 256>>>(fb, pl->omega, pl->scale, pl->d_tw4);
+            k_build_zt<<<4, 256>>>(fb, zeta, pl->d_zt);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_last_error("gfb_ntt_plan_create", e);
+        gfb_ntt_plan_destroy(pl);
+        return GFB_ERR_CUDA;
+    }
+    *out = pl;
+    return GFB_OK;
+}
+
+void gfb_ntt_plan_destroy(gfb_ntt_plan* pl) {
+    if (!pl) return;
+    if (pl->d_pow) cudaFree(pl->d_pow);
+    if (pl->d_tw4) cudaFree(pl->d_tw4);
+    if (pl->d_zt) cudaFree(pl->d_zt);
+    free(pl);
+}
+
+size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t batch) {
+    using namespace gfb;
+    (void)elem_bytes;
+    if (!pl || batch == 0) return 0;
+    if (pl->fast) {
+        const size_t rows = batch < (size_t)kNttChunk ? batch : (size_t)kNttChunk;
+        return rows * pl->n * sizeof(uint32_t);
+    }
+    if (pl->n <= 2) return 0;
+    size_t rows = kGenericWsBytes / (pl->n * sizeof(uint32_t));
+    if (rows == 0) rows = 1;
+    return 2 * rows * pl->n * sizeof(uint32_t);
+}
+
+gfb_status gfb_ntt_exec(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t batch, void* workspace, void* stream) {
+    using namespace gfb;
+    if (!pl) return GFB_ERR_BAD_ARG;
+    if (batch == 0) return GFB_OK;
+    if (!x || !y) return GFB_ERR_BAD_ARG;
+    if (eb != 4 && eb != 8) return GFB_ERR_BAD_ARG;
+    if (gfb_ntt_workspace_bytes(pl, eb, batch) != 0 && !workspace) return GFB_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->fast) {
+        uint32_t* ws = (uint32_t*)workspace;
+        if (eb == 4)
+            return pl->lazy ? run_fast_t<uint32_t, true>(pl, (const uint32_t*)x, (uint32_t*)y, batch, ws, st)
+                            : run_fast_t<uint32_t, false>(pl, (const uint32_t*)x, (uint32_t*)y, batch, ws, st);
+        return pl->lazy ? run_fast_t<unsigned long long, true>(pl, (const unsigned long long*)x, (unsigned long long*)y,
+                                                               batch, ws, st)
+                        : run_fast_t<unsigned long long, false>(pl, (const unsigned long long*)x,
+                                                                (unsigned long long*)y, batch, ws, st);
+    }
+    if (eb == 4) return run_generic_t<uint32_t>(pl, (const uint32_t*)x, (uint32_t*)y, batch, workspace, st);
+    return run_generic_t<unsigned long long>(pl, (const unsigned long long*)x, (unsigned long long*)y, batch, workspace,
+                                             st);
+}
+
+// Host pipeline: chunks of whole transforms rotate over the staging slots; each slot owns its workspace.
+gfb_status gfb_ntt_exec_host(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t batch) {
+    using namespace gfb;
+    if (!pl) return GFB_ERR_BAD_ARG;
+    if (batch == 0) return GFB_OK;
+    if (!x || !y || (eb != 4 && eb != 8)) return GFB_ERR_BAD_ARG;
+    HostPipeline* hp = HostPipeline::get();
+    if (!hp) return GFB_ERR_CUDA;
+    const size_t row_bytes = pl->n * (size_t)eb;
+    size_t rows = kChunkBytes / row_bytes;
+    if (rows == 0) rows = 1;
+    if (rows > batch) rows = batch;
+    const size_t ws_bytes = gfb_ntt_workspace_bytes(pl, eb, rows);
+    gfb_status status = GFB_OK;
+    for (size_t c = 0, off = 0; off < batch && status == GFB_OK; ++c, off += rows) {
+        const int slot = (int)(c % kSlots);
+        cudaStream_t st = hp->streams[slot];
+        const size_t cnt = batch - off < rows ? batch - off : rows;
+        void* dx = hp->buffer(slot, 0, rows * row_bytes);
+        void* dy = hp->buffer(slot, 1, rows * row_bytes);
+        void* dw = ws_bytes ? hp->buffer(slot, 2, ws_bytes) : nullptr;
+        if (!dx || !dy || (ws_bytes && !dw)) return GFB_ERR_CUDA;
+        GFB_CUDA_TRY(cudaMemcpyAsync(dx, (const char*)x + off * row_bytes, cnt * row_bytes, cudaMemcpyHostToDevice, st));
+        status = gfb_ntt_exec(pl, eb, dx, dy, cnt, dw, st);
+        if (status != GFB_OK) break;
+        GFB_CUDA_TRY(cudaMemcpyAsync((char*)y + off * row_bytes, dy, cnt * row_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e = hp->drain();
+    if (e != cudaSuccess) {
+        set_last_error("gfb_ntt_exec_host drain", e);
+        return GFB_ERR_CUDA;
+    }
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,594 @@
+// gfb_rs.cu — Reed-Solomon encode / errors-and-erasures decode over GF(2^m), m <= 8.
+//
+// One warp per codeword; EXP/LOG tables (uint8) and the log-domain parity matrix staged in shared
+// memory; every per-codeword polynomial lives in a per-warp shared-memory scratch area.
+//
+// Decode follows bch_decode_jit.implementation step by step
+// (/root/reference/src/galois/_codes/_bch.py:1337-1578) with the serial inner loops spread over the
+// 32 lanes: syndromes (:1370) → erasure locator Γ (:1389-1393) → modified syndromes (:1408-1409) →
+// Berlekamp-Massey (:1421-1428, _lfsr.py:1647-1702, same array sizes and update rules) → bound
+// check (:1431) → Λ_total (:1449) → Chien search (:1464-1481) → Ω' (:1498-1499) → Λ_total'
+// (:1512-1515) → Forney (:1536-1556) → correction (:1567-1576).  Failure leaves the row equal to
+// the received row and n_errors = -1 (:1344, :1359, :1432, :1480).
+//
+// Encode is the systematic product parity = message · P (_codes/_linear.py:270-284) with
+// P from _poly_to_generator_matrix (_codes/_cyclic.py:206-217), computed on the host at create time.
+//
+// Algorithmic bytes per codeword: encode ks + ns, decode 2*ns + 8 (+ ns with an erasure mask).
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "gfb_common.cuh"
+#include "gfb_host.cuh"
+
+struct gfb_rs_code {
+    gfb_field* field;
+    int n, k, d, c, m;
+    int q1;         // order - 1
+    int log_alpha;  // alpha = EXP[log_alpha]
+    std::vector<uint8_t> gen;   // d coefficients, degree-descending
+    std::vector<uint8_t> P;     // k x (n-k)
+    uint8_t* d_exp8;            // 2*order entries
+    uint8_t* d_log8;            // order entries
+    uint8_t* d_logP;            // k x (n-k), 255 = zero entry
+};
+
+namespace gfb {
+
+constexpr int kRsWarps = 8;
+constexpr int kRsThreads = kRsWarps * 32;
+constexpr int kMaxN = 256;
+constexpr int kScratchArrays = 14;
+
+struct RsDev {
+    int n, k, d, c, q1, log_alpha, order;
+    const uint8_t* exp8;
+    const uint8_t* log8;
+    const uint8_t* logP;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host-side GF(2^m) helpers on the field's uint16 tables
+// ------------------------------------------------------------------------------------------------
+struct HostGf {
+    const uint16_t* e;
+    const uint16_t* l;
+    int q1;
+    uint8_t mul(uint8_t a, uint8_t b) const { return (a && b) ? (uint8_t)e[l[a] + l[b]] : 0; }
+    uint8_t inv(uint8_t a) const { return (uint8_t)e[q1 - l[a]]; }
+    uint8_t pow_alpha(int la, long long x) const {
+        long long r = ((long long)la * x) % q1;
+        if (r < 0) r += q1;
+        return (uint8_t)e[r];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRsThreads) k_rs_encode(RsDev rs, const uint8_t* __restrict__ msg, int ks,
+                                                           uint8_t* __restrict__ cw, size_t N) {
+    extern __shared__ uint8_t smem[];
+    const int r = rs.n - rs.k;
+    uint8_t* s_exp = smem;                       // 2*order
+    uint8_t* s_log = s_exp + 2 * rs.order;       // order
+    uint8_t* s_logP = s_log + rs.order;          // k*r
+    uint8_t* s_msg = s_logP + rs.k * r;          // kRsWarps * kMaxN
+    for (int i = threadIdx.x; i < 2 * rs.order; i += blockDim.x) s_exp[i] = rs.exp8[i];
+    for (int i = threadIdx.x; i < rs.order; i += blockDim.x) s_log[i] = rs.log8[i];
+    for (int i = threadIdx.x; i < rs.k * r; i += blockDim.x) s_logP[i] = rs.logP[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* lmsg = s_msg + warp * kMaxN;  // LOG of the message symbols, 255 = zero symbol
+    const int pad = rs.k - ks;
+    const int ns = ks + r;
+    const size_t warps_total = (size_t)gridDim.x * kRsWarps;
+    for (size_t cwi = (size_t)blockIdx.x * kRsWarps + warp; cwi < N; cwi += warps_total) {
+        const uint8_t* mrow = msg + cwi * ks;
+        uint8_t* crow = cw + cwi * ns;
+        for (int i = lane; i < ks; i += 32) {
+            uint8_t v = mrow[i];
+            crow[i] = v;
+            lmsg[i] = v ? s_log[v] : 255;
+        }
+        __syncwarp();
+        for (int j = lane; j < r; j += 32) {
+            uint32_t acc = 0;
+            const uint8_t* col = s_logP + (size_t)pad * r + j;
+            for (int i = 0; i < ks; ++i) {
+                uint32_t lm = lmsg[i];
+                uint32_t lp = col[(size_t)i * r];
+                if (lm != 255u && lp != 255u) acc ^= s_exp[lm + lp];
+            }
+            crow[ks + j] = (uint8_t)acc;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+struct Gf8 {
+    const uint8_t* e;
+    const uint8_t* l;
+    int q1;
+    __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) const {
+        return (a && b) ? e[(uint32_t)l[a] + (uint32_t)l[b]] : 0u;
+    }
+    __device__ __forceinline__ uint32_t inv(uint32_t a) const { return e[q1 - l[a]]; }
+    // alpha^x for any integer x, given log(alpha)
+    __device__ __forceinline__ uint32_t pow_alpha(int la, int x) const {
+        int r = (int)(((long long)la * x) % q1);
+        if (r < 0) r += q1;
+        return e[r];
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_xor(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_t* __restrict__ received,
+                                                           const uint8_t* __restrict__ erasures, int ns,
+                                                           uint8_t* __restrict__ decoded, long long* __restrict__ n_errors,
+                                                           size_t N) {
+    extern __shared__ uint8_t smem[];
+    uint8_t* s_exp = smem;
+    uint8_t* s_log = s_exp + 2 * rs.order;
+    uint8_t* s_scratch = s_log + rs.order;
+    for (int i = threadIdx.x; i < 2 * rs.order; i += blockDim.x) s_exp[i] = rs.exp8[i];
+    for (int i = threadIdx.x; i < rs.order; i += blockDim.x) s_log[i] = rs.log8[i];
+    __syncthreads();
+    const Gf8 gf{s_exp, s_log, rs.q1};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* w = s_scratch + (size_t)warp * kScratchArrays * kMaxN;
+    uint8_t* rec = w + 0 * kMaxN;      // received, ascending degree, erasures zeroed
+    uint8_t* rlog = w + 1 * kMaxN;     // LOG(rec) or 255
+    uint8_t* epos = w + 2 * kMaxN;     // erasure positions (ascending degree index)
+    uint8_t* S = w + 3 * kMaxN;        // syndromes
+    uint8_t* gam = w + 4 * kMaxN;      // Γ, ascending
+    uint8_t* Sp = w + 5 * kMaxN;       // S'
+    uint8_t* C = w + 6 * kMaxN;        // BM connection polynomial
+    uint8_t* B = w + 7 * kMaxN;
+    uint8_t* T = w + 8 * kMaxN;
+    uint8_t* Lt = w + 9 * kMaxN;       // Λ_total, ascending
+    uint8_t* Om = w + 10 * kMaxN;      // Ω'
+    uint8_t* pos = w + 11 * kMaxN;     // error/erasure positions found by the Chien search
+    uint8_t* lam = w + 12 * kMaxN;     // Λ, ascending
+    uint8_t* tmp = w + 13 * kMaxN;
+    const int d1 = rs.d - 1;
+    const int la = rs.log_alpha;
+    const int q1 = rs.q1;
+    const size_t warps_total = (size_t)gridDim.x * kRsWarps;
+
+    for (size_t cwi = (size_t)blockIdx.x * kRsWarps + warp; cwi < N; cwi += warps_total) {
+        const uint8_t* rrow = received + cwi * ns;
+        const uint8_t* erow = erasures ? erasures + cwi * ns : nullptr;
+        uint8_t* drow = decoded + cwi * ns;
+        __syncwarp();
+        // ---- load; dec_codewords = codewords.copy() (:1344); received ascending; erasure positions in
+        //      ascending-degree order (:1351-1355)
+        int u = 0;
+        for (int base = 0; base < ns; base += 32) {
+            const int i = base + lane;  // ascending-degree index
+            uint32_t v = 0, er = 0;
+            if (i < ns) {
+                v = rrow[ns - 1 - i];
+                drow[ns - 1 - i] = (uint8_t)v;
+                er = erow ? (erow[ns - 1 - i] != 0) : 0u;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, er);
+            if (er) {
+                epos[u + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)i;
+                v = 0;
+            }
+            u += __popc(bal);
+            if (i < ns) {
+                rec[i] = (uint8_t)v;
+                rlog[i] = v ? s_log[v] : 255;
+            }
+        }
+        __syncwarp();
+        long long result = 0;
+        bool done = false;
+        if (u > d1) {  // :1357-1360
+            result = -1;
+            done = true;
+        }
+        // ---- 1. syndromes S_l = r(alpha^(c+l)), l = 0..d-2 (:1370)
+        uint32_t any_nz = 0;
+        if (!done) {
+            for (int l = lane; l < d1; l += 32) {
+                const int lr = (int)(((long long)la * (rs.c + l)) % q1);  // log of the root
+                int e = 0;                                                // lr * i mod q1 for i = 0
+                uint32_t acc = 0;
+                for (int i = 0; i < ns; ++i) {
+                    const uint32_t lg = rlog[i];
+                    if (lg != 255u) acc ^= s_exp[lg + (uint32_t)e];
+                    e += lr;
+                    if (e >= q1) e -= q1;
+                }
+                S[l] = (uint8_t)acc;
+                any_nz |= acc;
+            }
+            any_nz = __ballot_sync(0xffffffffu, any_nz != 0);
+            if (any_nz == 0 && u == 0) done = true;  // :1373-1376, result stays 0
+        }
+        __syncwarp();
+        int v = 0;
+        if (!done) {
+            // ---- 2. Γ(x) = prod (1 - Y_k x), Y_k = alpha^(e_k) (:1389-1393); lanes own coefficient indices
+            for (int i = lane; i <= d1; i += 32) gam[i] = (i == 0) ? 1 : 0;
+            __syncwarp();
+            for (int k = 0; k < u; ++k) {
+                const uint32_t Yk = gf.pow_alpha(la, (int)epos[k]);
+                // new[i] = old[i] + Yk * old[i-1], i = 0..k+1 ; read all, then write
+                uint32_t nv[8];
+                int cnt = 0;
+                for (int i = lane; i <= k + 1; i += 32) {
+                    uint32_t prev = i > 0 ? gam[i - 1] : 0u;
+                    nv[cnt++] = (uint32_t)gam[i] ^ gf.mul(Yk, prev);
+                }
+                __syncwarp();
+                cnt = 0;
+                for (int i = lane; i <= k + 1; i += 32) gam[i] = (uint8_t)nv[cnt++];
+                __syncwarp();
+            }
+            // ---- 3. S'(x) = Γ(x) S(x) mod x^(d-1) (:1408-1409)
+            for (int l = lane; l < d1; l += 32) {
+                uint32_t acc = 0;
+                const int imax = l < u ? l : u;
+                for (int i = 0; i <= imax; ++i) acc ^= gf.mul(gam[i], S[l - i]);
+                Sp[l] = (uint8_t)acc;
+            }
+            __syncwarp();
+            // ---- 4. Berlekamp-Massey on S'[u:] (:1421-1428; _lfsr.py:1647-1702)
+            int lam_len = 1;
+            if (u < d1) {
+                const uint8_t* Sq = Sp + u;
+                const int ls = d1 - u;  // S.size
+                for (int i = lane; i < ls; i += 32) {
+                    C[i] = (i == 0);
+                    B[i] = (i == 0);
+                }
+                __syncwarp();
+                int L = 0, mm = 1;
+                uint32_t b = 1;
+                for (int nn = 0; nn < ls; ++nn) {
+                    uint32_t dsc = 0;
+                    for (int i = lane; i <= L; i += 32) dsc ^= gf.mul(Sq[nn - i], C[i]);
+                    dsc = warp_xor(dsc);
+                    if (dsc == 0) {
+                        mm += 1;
+                    } else {
+                        const uint32_t dob = gf.mul(dsc, gf.inv(b));
+                        if (2 * L > nn) {
+                            for (int i = mm + lane; i < ls; i += 32) C[i] ^= (uint8_t)gf.mul(dob, B[i - mm]);
+                            mm += 1;
+                        } else {
+                            for (int i = lane; i < ls; i += 32) T[i] = C[i];
+                            __syncwarp();
+                            for (int i = mm + lane; i < ls; i += 32) C[i] ^= (uint8_t)gf.mul(dob, B[i - mm]);
+                            __syncwarp();
+                            for (int i = lane; i < ls; i += 32) B[i] = T[i];
+                            L = nn + 1 - L;
+                            b = dsc;
+                            mm = 1;
+                        }
+                    }
+                    __syncwarp();
+                }
+                // C = C[:L+1], trim high-degree zeros; Λ ascending = C
+                int len = L + 1 < ls ? L + 1 : ls;
+                int last = -1;
+                for (int i = lane; i < len; i += 32)
+                    if (C[i] != 0) last = i;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    int other = __shfl_xor_sync(0xffffffffu, last, o);
+                    last = other > last ? other : last;
+                }
+                lam_len = last >= 0 ? last + 1 : 1;
+                for (int i = lane; i < lam_len; i += 32) lam[i] = C[i];
+            } else {
+                if (lane == 0) lam[0] = 1;
+            }
+            __syncwarp();
+            v = lam_len - 1;
+            if (2 * v + u > d1) {  // :1431-1433
+                result = -1;
+                done = true;
+            }
+        }
+        if (!done) {
+            // ---- 5. Λ_total = Γ Λ (:1449); degree u + v <= d-1
+            const int lt_len = u + v + 1;
+            for (int j = lane; j < lt_len; j += 32) {
+                uint32_t acc = 0;
+                const int i0 = j - v > 0 ? j - v : 0;
+                const int i1 = j < u ? j : u;
+                for (int i = i0; i <= i1; ++i) acc ^= gf.mul(gam[i], lam[j - i]);
+                Lt[j] = (uint8_t)acc;
+                tmp[j] = acc ? s_log[acc] : 255;  // log Λ_total
+            }
+            __syncwarp();
+            // ---- 6. Chien search over i = 0..design_n-1: Λ_total(alpha^-i) == 0 (:1464-1475)
+            int v_total = 0;
+            for (int base = 0; base < rs.n; base += 32) {
+                const int i = base + lane;
+                uint32_t val = 1;  // non-zero placeholder for out-of-range lanes
+                if (i < rs.n) {
+                    // log of X_i^-1 = (-la * i) mod q1
+                    int lx = (int)(((long long)la * i) % q1);
+                    lx = lx ? q1 - lx : 0;
+                    int e = 0;
+                    val = 0;
+                    for (int j = 0; j < lt_len; ++j) {
+                        const uint32_t lg = tmp[j];
+                        if (lg != 255u) val ^= s_exp[lg + (uint32_t)e];
+                        e += lx;
+                        if (e >= q1) e -= q1;
+                    }
+                }
+                const bool root = (i < ns) && (val == 0);  // roots at i >= n are not recorded (:1469-1472)
+                const uint32_t bal = __ballot_sync(0xffffffffu, root);
+                if (root) {
+                    const int slot = v_total + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < kMaxN) pos[slot] = (uint8_t)i;
+                }
+                v_total += __popc(bal);
+            }
+            __syncwarp();
+            if (v_total != v + u) {  // :1479-1481
+                result = -1;
+                done = true;
+            }
+            if (!done) {
+                // ---- 7. Ω' = Λ S' mod x^(d-1) (:1498-1499)
+                for (int l = lane; l < d1; l += 32) {
+                    uint32_t acc = 0;
+                    const int imax = l < v ? l : v;
+                    for (int i = 0; i <= imax; ++i) acc ^= gf.mul(lam[i], Sp[l - i]);
+                    Om[l] = (uint8_t)acc;
+                }
+                __syncwarp();
+                // ---- 8./9. Forney (:1512-1556): E = Ω'(X^-1) / Λ_total'(X^-1) * (X^-1)^(c-1); characteristic 2:
+                //      Λ_total'(x) keeps the odd-degree terms, and negation is the identity.
+                for (int r = lane; r < v_total; r += 32) {
+                    const int i = pos[r];
+                    int lx = (int)(((long long)la * i) % q1);
+                    lx = lx ? q1 - lx : 0;
+                    const uint32_t Xinv = s_exp[lx];
+                    uint32_t num = 0, den = 0;
+                    // Horner, highest degree first
+                    for (int j = d1 - 1; j >= 0; --j) num = gf.mul(num, Xinv) ^ Om[j];
+                    for (int j = lt_len - 1; j >= 1; --j) den = gf.mul(den, Xinv) ^ ((j & 1) ? Lt[j] : 0u);
+                    uint32_t E = 0;
+                    if (den != 0) {
+                        E = gf.mul(num, gf.inv(den));
+                        // (X^-1)^(c-1)
+                        int ex = (int)(((long long)lx * (rs.c - 1)) % q1);
+                        if (ex < 0) ex += q1;
+                        E = gf.mul(E, s_exp[ex]);
+                    }
+                    // ---- 10. correct (:1567-1576)
+                    rec[i] ^= (uint8_t)E;
+                }
+                __syncwarp();
+                for (int i = lane; i < ns; i += 32) drow[ns - 1 - i] = rec[i];
+                result = v;
+            }
+        }
+        if (lane == 0) n_errors[cwi] = result;
+    }
+}
+
+static RsDev make_dev(const gfb_rs_code* rs) {
+    RsDev d;
+    d.n = rs->n;
+    d.k = rs->k;
+    d.d = rs->d;
+    d.c = rs->c;
+    d.q1 = rs->q1;
+    d.log_alpha = rs->log_alpha;
+    d.order = rs->q1 + 1;
+    d.exp8 = rs->d_exp8;
+    d.log8 = rs->d_log8;
+    d.logP = rs->d_logP;
+    return d;
+}
+
+static int rs_grid(size_t N) {
+    size_t want = (N + kRsWarps - 1) / kRsWarps;
+    size_t cap = (size_t)sm_count() * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace gfb
+
+extern "C" {
+
+gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha) {
+    using namespace gfb;
+    if (!out) return GFB_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!f || f->kind != GFB_BINARY) return GFB_ERR_BAD_ARG;
+    if (f->degree > 8 || !f->h_exp) return GFB_ERR_UNSUPPORTED;
+    const int order = 1 << f->degree;
+    const int q1 = order - 1;
+    if (n < 1 || n > q1 || k < 1 || k > n || c < 0 || (q1 % n) != 0) return GFB_ERR_BAD_ARG;
+    if (alpha == 0 || alpha >= (uint64_t)order) return GFB_ERR_BAD_ARG;
+    gfb_rs_code* rs = new gfb_rs_code();
+    rs->field = f;
+    rs->n = n;
+    rs->k = k;
+    rs->d = n - k + 1;
+    rs->c = c;
+    rs->m = f->degree;
+    rs->q1 = q1;
+    rs->log_alpha = f->h_log[alpha];
+    rs->d_exp8 = rs->d_log8 = rs->d_logP = nullptr;
+    HostGf gf{f->h_exp, f->h_log, q1};
+    const int r = n - k;
+    // g(x) = prod_{i=0}^{d-2} (x - alpha^(c+i)), degree-descending (_reed_solomon.py:206-207)
+    rs->gen.assign(rs->d, 0);
+    rs->gen[0] = 1;
+    int len = 1;
+    for (int i = 0; i < rs->d - 1; ++i) {
+        uint8_t root = gf.pow_alpha(rs->log_alpha, c + i);
+        rs->gen[len] = 0;
+        for (int j = len; j >= 1; --j) rs->gen[j] ^= gf.mul(rs->gen[j - 1], root);
+        len += 1;
+    }
+    // systematic parity block P (_codes/_cyclic.py:206-217)
+    rs->P.assign((size_t)k * (r > 0 ? r : 1), 0);
+    if (r > 0) {
+        const uint8_t g_last_inv = gf.inv(rs->gen[r]);
+        for (int j = 0; j < r; ++j) rs->P[j] = gf.mul(rs->gen[j], g_last_inv);
+        for (int i = 1; i < k; ++i) {
+            uint8_t* row = &rs->P[(size_t)i * r];
+            const uint8_t* prev = &rs->P[(size_t)(i - 1) * r];
+            row[0] = 0;
+            for (int j = 1; j < r; ++j) row[j] = prev[j - 1];
+            const uint8_t last = prev[r - 1];
+            if (last)
+                for (int j = 0; j < r; ++j) row[j] ^= gf.mul(last, rs->P[j]);
+        }
+    }
+    std::vector<uint8_t> exp8(2 * order), log8(order), logP((size_t)k * (r > 0 ? r : 1));
+    for (int i = 0; i < 2 * order; ++i) exp8[i] = (uint8_t)f->h_exp[i];
+    for (int i = 0; i < order; ++i) log8[i] = (uint8_t)f->h_log[i];
+    for (size_t i = 0; i < logP.size(); ++i) logP[i] = rs->P[i] ? (uint8_t)f->h_log[rs->P[i]] : 255;
+    cudaError_t e = cudaMalloc((void**)&rs->d_exp8, exp8.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->d_log8, log8.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->d_logP, logP.size());
+    if (e == cudaSuccess) e = cudaMemcpy(rs->d_exp8, exp8.data(), exp8.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(rs->d_log8, log8.data(), log8.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(rs->d_logP, logP.data(), logP.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_last_error("gfb_rs_create upload", e);
+        gfb_rs_destroy(rs);
+        return GFB_ERR_CUDA;
+    }
+    *out = rs;
+    return GFB_OK;
+}
+
+void gfb_rs_destroy(gfb_rs_code* rs) {
+    if (!rs) return;
+    if (rs->d_exp8) cudaFree(rs->d_exp8);
+    if (rs->d_log8) cudaFree(rs->d_log8);
+    if (rs->d_logP) cudaFree(rs->d_logP);
+    delete rs;
+}
+
+gfb_status gfb_rs_get_generator_poly(const gfb_rs_code* rs, uint8_t* g) {
+    if (!rs || !g) return GFB_ERR_BAD_ARG;
+    memcpy(g, rs->gen.data(), rs->d);
+    return GFB_OK;
+}
+
+gfb_status gfb_rs_get_parity_matrix(const gfb_rs_code* rs, uint8_t* P) {
+    if (!rs || !P) return GFB_ERR_BAD_ARG;
+    memcpy(P, rs->P.data(), (size_t)rs->k * (rs->n - rs->k));
+    return GFB_OK;
+}
+
+gfb_status gfb_rs_encode(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* cw, size_t N, void* stream) {
+    using namespace gfb;
+    if (!rs || !msg || !cw) return N == 0 && rs ? GFB_OK : GFB_ERR_BAD_ARG;
+    if (ks < 1 || ks > rs->k) return GFB_ERR_BAD_ARG;
+    if (N == 0) return GFB_OK;
+    RsDev d = make_dev(rs);
+    const int r = rs->n - rs->k;
+    const size_t smem = 3 * (size_t)d.order + (size_t)rs->k * r + (size_t)kRsWarps * kMaxN;
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_rs_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rs_encode<<<rs_grid(N), kRsThreads, smem, (cudaStream_t)stream>>>(d, msg, ks, cw, N);
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t* erasures, int ns, uint8_t* decoded,
+                         int64_t* n_errors, size_t N, void* stream) {
+    using namespace gfb;
+    if (!rs || !received || !decoded || !n_errors) return N == 0 && rs ? GFB_OK : GFB_ERR_BAD_ARG;
+    if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
+    if (N == 0) return GFB_OK;
+    RsDev d = make_dev(rs);
+    const size_t smem = 3 * (size_t)d.order + (size_t)kRsWarps * kScratchArrays * kMaxN;
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_rs_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rs_decode<<<rs_grid(N), kRsThreads, smem, (cudaStream_t)stream>>>(d, received, erasures, ns, decoded,
+                                                                         (long long*)n_errors, N);
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+// ---- host pipelines: chunks of codewords rotate over the staging slots (gfb_host.cuh)
+gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* cw, size_t N) {
+    using namespace gfb;
+    if (!rs || !msg || !cw) return N == 0 && rs ? GFB_OK : GFB_ERR_BAD_ARG;
+    if (ks < 1 || ks > rs->k) return GFB_ERR_BAD_ARG;
+    HostPipeline* hp = HostPipeline::get();
+    if (!hp) return GFB_ERR_CUDA;
+    const size_t ns = (size_t)ks + (rs->n - rs->k);
+    const size_t chunk = kChunkBytes / kMaxN;  // codewords per chunk
+    gfb_status status = GFB_OK;
+    for (size_t c = 0, off = 0; off < N && status == GFB_OK; ++c, off += chunk) {
+        const int slot = (int)(c % kSlots);
+        cudaStream_t st = hp->streams[slot];
+        const size_t cnt = N - off < chunk ? N - off : chunk;
+        uint8_t* dm = (uint8_t*)hp->buffer(slot, 0, chunk * kMaxN);
+        uint8_t* dc = (uint8_t*)hp->buffer(slot, 1, chunk * kMaxN);
+        if (!dm || !dc) return GFB_ERR_CUDA;
+        GFB_CUDA_TRY(cudaMemcpyAsync(dm, msg + off * ks, cnt * ks, cudaMemcpyHostToDevice, st));
+        status = gfb_rs_encode(rs, dm, ks, dc, cnt, st);
+        if (status != GFB_OK) break;
+        GFB_CUDA_TRY(cudaMemcpyAsync(cw + off * ns, dc, cnt * ns, cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e = hp->drain();
+    if (e != cudaSuccess) {
+        set_last_error("gfb_rs_encode_host drain", e);
+        return GFB_ERR_CUDA;
+    }
+    return status;
+}
+
+gfb_status gfb_rs_decode_host(gfb_rs_code* rs, const uint8_t* received, const uint8_t* erasures, int ns,
+                              uint8_t* decoded, int64_t* n_errors, size_t N) {
+    using namespace gfb;
+    if (!rs || !received || !decoded || !n_errors) return N == 0 && rs ? GFB_OK : GFB_ERR_BAD_ARG;
+    if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
+    HostPipeline* hp = HostPipeline::get();
+    if (!hp) return GFB_ERR_CUDA;
+    const size_t chunk = kChunkBytes / kMaxN;
+    gfb_status status = GFB_OK;
+    for (size_t c = 0, off = 0; off < N && status == GFB_OK; ++c, off += chunk) {
+        const int slot = (int)(c % kSlots);
+        cudaStream_t st = hp->streams[slot];
+        const size_t cnt = N - off < chunk ? N - off : chunk;
+        uint8_t* dr = (uint8_t*)hp->buffer(slot, 0, chunk * kMaxN);
+        uint8_t* de = (uint8_t*)hp->buffer(slot, 1, chunk * kMaxN);
+        uint8_t* dd = (uint8_t*)hp->buffer(slot, 2, chunk * kMaxN);
+        int64_t* dn = (int64_t*)hp->buffer(slot, 3, chunk * sizeof(int64_t));
+        if (!dr || !de || !dd || !dn) return GFB_ERR_CUDA;
+        GFB_CUDA_TRY(cudaMemcpyAsync(dr, received + off * ns, cnt * ns, cudaMemcpyHostToDevice, st));
+        if (erasures) GFB_CUDA_TRY(cudaMemcpyAsync(de, erasures + off * ns, cnt * ns, cudaMemcpyHostToDevice, st));
+        status = gfb_rs_decode(rs, dr, erasures ? de : nullptr, ns, dd, dn, cnt, st);
+        if (status != GFB_OK) break;
+        GFB_CUDA_TRY(cudaMemcpyAsync(decoded + off * ns, dd, cnt * ns, cudaMemcpyDeviceToHost, st));
+        GFB_CUDA_TRY(cudaMemcpyAsync(n_errors + off, dn, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e = hp->drain();
+    if (e != cudaSuccess) {
+        set_last_error("gfb_rs_decode_host drain", e);
+        return GFB_ERR_CUDA;
+    }
+    return status;
+}
+
+}  // extern "C"

@@ -17,7 +17,7 @@
  *   - element storage is native width: elem_bytes ∈ {1,2,4,8} (the reference's
  *     dtypes uint8/uint16/uint32/int8/int16/int32/int64, _domains/_meta.py:19;
  *     values are always non-negative so signedness does not matter), or 16 for
- *     GF(2^m), 64 < m <= 128 (two little-endian uint64 limbs per element; the
+ *     GF(2^m), 64 <= m <= 128 (two little-endian uint64 limbs per element; the
  *     reference holds these as Python ints in dtype=object arrays).
  *   - every function returns a gfb_status; nothing throws across the boundary.
  *   - "zero division" (reference: ZeroDivisionError raised from inside the Numba

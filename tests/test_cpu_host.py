@@ -1,0 +1,142 @@
+"""
+CPU-only tests (``-m "not gpu"``): host logic of the mirror (field construction, number theory, argument
+checking) and that the C-ABI library loads and exports every symbol include/galois_b200.h declares.
+No compute call is made: without a GPU the product path must fail loudly, never fall back.
+"""
+
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import galois_b200 as gb
+from galois_b200 import _lib, _nt
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "galois_b200.h").read_text()
+    declared = set(re.findall(r"\b(gfb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gfb_field", "gfb_ntt_plan", "gfb_rs_code"}
+    assert len(declared) >= 30
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libgalois_b200.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.gfb_version()
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    GF = gb.GF(31)
+    x = GF([1, 2, 3])
+    with pytest.raises(gb.BackendUnavailable):
+        x * x
+    with pytest.raises(gb.BackendUnavailable):
+        gb.ntt([1, 2, 3, 4], modulus=5)
+
+
+def test_product_never_imports_oracle():
+    for path in (ROOT / "galois_b200").rglob("*.py"):
+        text = path.read_text()
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), path
+    for path in (ROOT / "galois_b200" / "csrc").glob("*"):
+        assert "oracle" not in path.read_text(), path
+
+
+def test_number_theory_matches_reference_constants(live_ntt, live_rs, live_elementwise):
+    _, meta = live_ntt
+    for key, m in meta.items():
+        if "seed" in key:
+            continue
+        p = int(key.split("/")[0][1:])
+        n = int(key.split("/")[1][1:])
+        assert _nt.primitive_root(p) == m["primitive_element"]
+        if n > 1:
+            assert int(gb.GF(p).primitive_root_of_unity(n)) == m["omega"]
+    assert _nt.primitive_root(2**31 - 1) == 7  # tests/fields/data/GF(2147483647)/properties.json
+    assert _nt.primitive_root(998244353) == 3
+    _, emeta = live_elementwise
+    for name, m in emeta.items():
+        deg = int(re.match(r"GF\(2\^(\d+)\)", name).group(1))
+        assert _nt.CONWAY_2[deg] == m["irreducible_poly"]
+        assert m["primitive_element"] == 2
+        assert _nt.is_irreducible2(_nt.CONWAY_2[deg])
+    assert _nt.is_primitive_element2(2, _nt.CONWAY_2[16])
+    assert not _nt.is_irreducible2(0b10001)  # x^4 + 1
+    assert _nt.factors(2**31 - 2) == ((2, 3, 7, 11, 31, 151, 331), (1, 2, 1, 1, 1, 1, 1))
+    assert _nt.prime_factors_with_multiplicity(176) == [2, 2, 2, 2, 11]
+    assert _nt.is_prime(998244353) and not _nt.is_prime(998244351)
+    assert _nt.parse_poly2("x^8 + x^4 + x^3 + x^2 + 1") == 0x11D
+
+
+def test_field_factory_and_array_construction():
+    GF = gb.GF(2**31 - 1)
+    assert gb.GF(2**31 - 1) is GF  # flyweight (_fields/_factory.py:385)
+    assert GF.characteristic == 2**31 - 1 and GF.degree == 1 and GF.order == 2**31 - 1
+    assert [np.dtype(d).name for d in GF.dtypes] == ["uint32", "int32", "int64"]  # _fields/_ufunc.py:36-48
+    assert int(GF.primitive_element) == 7
+    x = GF.Random(10, seed=1)
+    assert type(x) is GF and x.dtype == np.uint32
+    want = np.random.default_rng(1).integers(0, GF.order, 10, dtype=np.uint32)  # _domains/_array.py:278-280
+    assert np.array_equal(np.asarray(x), want)
+    assert np.array_equal(np.asarray(GF.Zeros(3)), [0, 0, 0]) and np.array_equal(np.asarray(GF.Ones(2)), [1, 1])
+    with pytest.raises(ValueError):
+        GF([GF.order])
+    with pytest.raises(TypeError):
+        GF([1.5])
+    with pytest.raises(TypeError):
+        GF([1, 2], dtype=np.uint8)
+    G8 = gb.GF(2**8)
+    assert G8.irreducible_poly == 0x11D and int(G8.primitive_element) == 2
+    assert [np.dtype(d).name for d in G8.dtypes] == ["uint8", "uint16", "uint32", "int16", "int32", "int64"]
+    with pytest.raises(LookupError):
+        gb.GF(2**128)  # no Conway polynomial of degree 128, as in the reference
+    G128 = gb.GF(2**128, irreducible_poly="x^128 + x^7 + x^2 + x + 1", primitive_element=2, verify=False)
+    assert G128.dtypes == [np.object_]
+    v = G128([1 << 127, 3])
+    assert np.array_equal(G128.from_limbs(v.to_limbs()), v)
+    with pytest.raises(ValueError):
+        gb.GF(2**4, irreducible_poly=0b10001)
+    with pytest.raises(ValueError):
+        gb.GF(6)
+    with pytest.raises(NotImplementedError):
+        gb.GF(3**4)
+    # comparisons / views behave like ndarrays
+    a = GF([1, 2, 3])
+    assert (a == GF([1, 5, 3])).tolist() == [True, False, True]
+    assert type(a[1:]) is GF and type(a.reshape(3, 1)) is GF
+
+
+def test_reed_solomon_constructor_checks():
+    rs = gb.ReedSolomon(255, 223)
+    assert (rs.n, rs.k, rs.d, rs.t) == (255, 223, 33, 16)
+    assert rs.field.irreducible_poly == 0x11D and int(rs.alpha) == 2 and rs.c == 1
+    assert rs.is_primitive and rs.is_narrow_sense and rs.is_systematic
+    assert gb.ReedSolomon(255, d=33).k == 223
+    assert gb.ReedSolomon(15, 9).field.order == 16
+    with pytest.raises(ValueError):
+        gb.ReedSolomon(255, 223, 30)
+    with pytest.raises(ValueError):
+        gb.ReedSolomon(255)
+    with pytest.raises(TypeError):
+        gb.ReedSolomon(255.0, 223)
+    with pytest.raises(ValueError):
+        gb.ReedSolomon(255, 223, c=-1)
+    assert np.array_equal(np.asarray(rs.roots)[:4], [2, 4, 8, 16])
+
+
+def test_ntt_argument_checks_need_no_gpu():
+    with pytest.raises(TypeError):
+        gb.ntt(1)
+    with pytest.raises(ValueError):
+        gb.ntt([1, 2, 3, 4], size=3)
+    with pytest.raises(ValueError):
+        gb.ntt([1, 2, 3, 40], modulus=43)
+    with pytest.raises(ValueError):
+        gb.ntt([1, 2, 3, 4], modulus=3 * 256 + 2)
