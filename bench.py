@@ -490,10 +490,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gfp_mul", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="ntt: total transforms; rs_decode: total codewords")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads in the default run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -506,7 +507,12 @@ def main():
 
     rank, world, local = dist_setup(args.gpus)
     cls = WORKLOADS[args.workload]
-    work = cls(rank, world)
+    kw = {}
+    if args.batch is not None and cls is Ntt:
+        kw["batch"] = args.batch
+    if args.batch is not None and cls is RsDecode:
+        kw["total"] = args.batch
+    work = cls(rank, world, **kw)
 
     sampler = ClockSampler(local)
     if rank == 0:

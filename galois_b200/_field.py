@@ -762,7 +762,7 @@ def GF(order, *, irreducible_poly=None, primitive_element=None, verify=True, com
                 f"GF({p}): primes >= 2^32 run in the reference's object-dtype 'python-calculate' mode and are "
                 "outside the CUDA hot path (SURVEY.md §8a)."
             )
-        poly = None
+        poly = p + ((p - alpha) % p)  # x - alpha, integer representation (the reference's GF(p).irreducible_poly)
         key = (p, 1, alpha)
     else:
         if p != 2:
