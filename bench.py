@@ -248,15 +248,18 @@ class Ntt:
 
         self.gb, self.torch = gb, torch
         self.GF = gb.GF(P_NTT)
+        from galois_b200._dist import shard_bounds
+
         self.batch_total = batch
-        self.rows = batch // world
+        lo, hi = shard_bounds(batch, rank, world)
+        self.rows = hi - lo
         self.name = f"NTT 2^20 over GF(998244353), batch {batch} sharded over {world} GPU(s) (BASELINE configs[2])"
         g = torch.Generator(device="cuda").manual_seed(3 + rank)
         x = torch.randint(0, P_NTT, (self.rows, self.N), dtype=torch.int32, device="cuda", generator=g)
         self.x = gb.DeviceArray(self.GF, x.view(torch.uint8).reshape(-1), (self.rows, self.N), np.uint32)
         self.out = gb.DeviceArray.empty(self.GF, (self.rows, self.N), np.uint32)
         self.units_per_step = self.rows
-        self.launches_per_step = 2 * ((self.rows + 15) // 16)
+        self.launches_per_step = 2 * ((self.rows + 73) // 74)  # pass 1 + pass 2 per chunk of 74 transforms
         self.h2d = self.d2h = 0
 
     def step(self):
@@ -307,8 +310,11 @@ class RsDecode:
         import galois_b200 as gb
 
         self.gb, self.torch = gb, torch
+        from galois_b200._dist import shard_bounds
+
         self.rs = gb.ReedSolomon(255, 223)
-        self.N = total // world
+        lo, hi = shard_bounds(total, rank, world)
+        self.N = hi - lo
         self.name = f"RS(255,223) decode, {total} codewords x 16 errors sharded over {world} GPU(s) (BASELINE configs[4])"
         GF = self.rs.field
         M = GF.Random((self.N, 223), seed=6 + rank)
@@ -495,6 +501,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gfp_mul", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="ntt: total transforms; rs_decode: total codewords")
+    ap.add_argument("--gather", action="store_true", help="N>1: also time the final all-gather of the result shards")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads in the default run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -524,8 +531,35 @@ def main():
     launches = args.steps * work.launches_per_step
     per_gpu_units = work.units_per_step
 
-    total_units = work.units_per_step * world * args.steps
+    # whole-job units per step: per-rank shards may differ by one row when the batch does not divide evenly
+    units_all = work.units_per_step
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([work.units_per_step], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        units_all = int(t.item())
+    total_units = units_all * args.steps
     value = total_units / (ms / 1e3)
+
+    # optional: the final gather of the result shards (the only collective of the path), timed on its own
+    gather_ms = None
+    if args.gather and world > 1 and hasattr(work, "out"):
+        from galois_b200._dist import gather_rows
+
+        rows_total = getattr(work, "batch_total", None)
+        if rows_total is not None:
+            flat = work.out.tensor.view(work.rows, -1)
+            for _ in range(2):
+                gather_rows(flat, rows_total)
+            barrier_sync(world)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            full = gather_rows(flat, rows_total)
+            g1.record()
+            barrier_sync(world)
+            gather_ms = max_over_ranks(g0.elapsed_time(g1), world)
+            del full
     peak, peak_src = measured_hbm_peak()
     # dominant kernel: algorithmic bytes of one step on this rank / mean device time of one step
     achieved = work.units_per_step * cls.bytes_per_unit / (ms / 1e3 / args.steps) / 1e9
@@ -593,6 +627,8 @@ def main():
                      "algorithmic_bytes_per_unit": cls.bytes_per_unit},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    if gather_ms is not None:
+        line["final_gather_ms"] = gather_ms
     if extras:
         line["extras"] = extras
     print(json.dumps(line), flush=True)

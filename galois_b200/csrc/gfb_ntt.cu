@@ -15,8 +15,7 @@
 //      pass 2  : tile of 16 rows x 1024 → shared memory, same warp NTT, transposed store
 //                X[k1 + 1024*k2].
 //    Butterflies are Harvey lazy butterflies with Shoup twiddles (values in [0,4p) when p < 2^30).
-//    Work is issued in chunks of kChunk transforms so that the workspace (64 MiB) stays L2-resident
-//    between the two passes: HBM traffic approaches the compulsory 8 B/element (4-byte storage).
+//    Work is issued in chunks of kNttChunk transforms (bounded uint32 workspace, whole waves of CTAs).
 //  * generic path, any N = 2^k <= 2^24, any p < 2^32: one Stockham autosort radix-2 stage per
 //    launch, ping-ponging between two workspaces (mirrors the reference's own stage structure).
 //
@@ -45,7 +44,7 @@ struct gfb_ntt_plan {
 
 namespace gfb {
 
-constexpr int kNttChunk = 16;              // transforms per pass-1/pass-2 launch pair (64 MiB workspace)
+constexpr int kNttChunk = 74;              // transforms per pass-1/pass-2 launch pair: 74*64 CTAs = 16 full waves of 2 CTAs/SM x 148 SMs
 constexpr size_t kGenericWsBytes = (size_t)64 << 20;
 
 // ------------------------------------------------------------------------------------------------
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
     const int c0 = (blockIdx.x & 63) * kTileW;
     const T* src = x + (transform << 20) + c0;
     uint32_t* dst = ws + (transform << 20) + c0;
-#pragma unroll 8
+#pragma unroll 16
     for (int it = 0; it < 64; ++it) {
         const int e = it * kFastThreads + threadIdx.x;
         const int w = e & 15, r = e >> 4;
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
     const int k1_0 = (blockIdx.x & 63) * kTileW;
     const uint32_t* src = ws + (transform << 20) + (size_t)k1_0 * 1024;
     T* dst = y + (transform << 20) + k1_0;
-#pragma unroll 8
+#pragma unroll 16
     for (int it = 0; it < 64; ++it) {
         const int e = it * kFastThreads + threadIdx.x;
         const int i = e & 1023, w = e >> 10;
@@ -304,7 +303,7 @@ static int ntt_occupancy() {
     static int occ = 0;
     if (occ == 0) {
         const char* e = getenv("GFB_NTT_OCC");
-        occ = (e && e[0] == '2') ? 2 : 3;
+        occ = (e && e[0] == '3') ? 3 : 2;
     }
     return occ;
 }
