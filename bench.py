@@ -50,13 +50,14 @@ def measured_hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic(kernel_key: str):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/*traffic*.json), or None."""
+def recorded_traffic(kernel_key: str, units_per_step: int):
+    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed
+    `ncu --set full` capture, profiles/*traffic*.json, times the units one step processes), or None."""
     for f in sorted((ROOT / "profiles").glob("*traffic*.json"), reverse=True):
         try:
             d = json.load(open(f))
             if kernel_key in d:
-                return d[kernel_key]
+                return d[kernel_key]["dram_bytes_per_unit"] * units_per_step
         except Exception:
             continue
     return None
@@ -623,8 +624,9 @@ def main():
         "config": {"workload": workload_name, "parallelism": f"shard{world}",
                    "l2": "inputs larger than L2 (no flush needed)", "units_per_gpu_per_step": per_gpu_units},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.workload), "kernel": cls.kernel, "peak_source": peak_src,
-                     "algorithmic_bytes_per_unit": cls.bytes_per_unit},
+                     "traffic": recorded_traffic(args.workload, per_gpu_units), "kernel": cls.kernel, "peak_source": peak_src,
+                     "algorithmic_bytes_per_unit": cls.bytes_per_unit,
+                     "algorithmic_bytes_per_step": cls.bytes_per_unit * per_gpu_units},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     if gather_ms is not None:

@@ -103,7 +103,10 @@ def _ntt(x, size=None, modulus=None, forward=True, scaled=True):
             raise TypeError(f"Argument {name!r} must be an int, not {type(v)}.")
     if size is None:
         size = np.shape(x)[-1] if isinstance(x, np.ndarray) else len(x)
-    xmax = int(np.max(x)) if np.size(x) else 0
+    if isinstance(x, FieldArray) and modulus is not None and type(x).characteristic == modulus:
+        xmax = 0  # elements of a GF(modulus) array are < modulus by construction: skip the O(n) scan
+    else:
+        xmax = int(np.max(x)) if np.size(x) else 0
     if modulus is None:
         m = int(np.ceil(xmax / size))
         m = max(m, 1)
