@@ -301,6 +301,8 @@ class Ntt:
 class RsDecode:
     """BASELINE configs[4]: RS(255,223) decode of codewords with 16 symbol errors each (t = 16)."""
 
+    n_err, n_era = 16, 0
+
     metric, unit, dtype, scaling = "rs255_223_decode_cw_per_sec", "codeword/s", "u8", "strong"
     kernel = "k_rs_decode"
     bytes_per_unit = 518
@@ -322,32 +324,40 @@ class RsDecode:
         dC = self.rs.encode_device(M.to_device())
         C = dC.tensor.view(self.N, 255)
         g = torch.Generator(device="cuda").manual_seed(7 + rank)
-        # 16 distinct positions per row: top-16 of random keys
+        # distinct positions per row: top-k of random keys; the first n_err get a non-zero error, the rest are erased
+        tot = self.n_err + self.n_era
         keys = torch.rand((self.N, 255), device="cuda", generator=g)
-        pos = keys.topk(16, dim=1).indices
-        err = torch.randint(1, 256, (self.N, 16), device="cuda", generator=g, dtype=torch.int32).to(torch.uint8)
+        pos = keys.topk(tot, dim=1).indices
+        err = torch.randint(1, 256, (self.N, tot), device="cuda", generator=g, dtype=torch.int32).to(torch.uint8)
         R = C.clone()
         R.scatter_(1, pos, R.gather(1, pos) ^ err)
+        self.E = None
+        if self.n_era:
+            E = torch.zeros((self.N, 255), dtype=torch.uint8, device="cuda")
+            E.scatter_(1, pos[:, self.n_err:], 1)
+            self.E = E
         self.C = C
         self.R = gb.DeviceArray(GF, R.reshape(-1), (self.N, 255), np.uint8)
+        self.name = self.name.replace("x 16 errors", f"x {self.n_err} errors + {self.n_era} erasures")
         self.units_per_step = self.N
         self.launches_per_step = 1
         self.h2d = self.d2h = 0
 
     def step(self):
-        self.dec, self.nerr = self.rs.decode_device(self.R)
+        self.dec, self.nerr = self.rs.decode_device(self.R, erasures=self.E)
 
     def check(self):
-        assert bool((self.nerr == 16).all()), "not every codeword reported 16 corrected errors"
+        assert bool((self.nerr == self.n_err).all()), "not every codeword reported the injected number of errors"
         assert bool((self.dec.tensor.view(self.N, 255) == self.C).all()), "decoded codewords differ from the originals"
 
     def e2e_setup(self):
         self.hR = self.R.cpu()
-        self.h2d, self.d2h = 255 * self.N, 255 * self.N + 8 * self.N
+        self.hE = self.E.cpu().numpy().astype(bool) if self.E is not None else None
+        self.h2d, self.d2h = 255 * self.N * (2 if self.E is not None else 1), 255 * self.N + 8 * self.N
         self.e2e_units = self.N
 
     def e2e_step(self):
-        self.hz = self.rs.decode(self.hR, output="codeword", errors=True)
+        self.hz = self.rs.decode(self.hR, erasures=self.hE, output="codeword", errors=True)
 
     def cpu_step(self, threads):
         import oracle
@@ -356,7 +366,8 @@ class RsDecode:
         if not hasattr(self, "ors"):
             self.ors = oracle.ReedSolomon(oracle.Field.binary(8, 0x11D, alpha=2), 255, 223)
             self.cR = np.asarray(self.R.cpu())[:n].astype(np.int64)
-        self.ors.decode(self.cR, threads=threads)
+            self.cE = self.E[:n].cpu().numpy() if self.E is not None else None
+        self.ors.decode(self.cR, self.cE, threads=threads)
         return len(self.cR)
 
     cpu_sample = "250 codewords per thread with 16 errors each (bch_decode_jit restatement, codewords over OpenMP threads)"
@@ -421,7 +432,229 @@ class Gf128Mul:
     cpu_sample = "2e5 elements per thread, shift-and-xor multiply on 128-bit integers (the reference itself runs this field on Python ints)"
 
 
+class Ewise:
+    """Generic element-wise workload: one ufunc over n-element arrays of one field / dtype (device-resident)."""
+
+    scaling = "weak"
+    field_order, field_kw, op, np_dtype, n, dtype = P_M31, {}, "mul", np.int64, 10**8, "int64"
+    metric, unit = "gfp_op_per_sec", "field-op/s"
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200 import _lib
+
+        self.gb, self.torch, self._lib = gb, torch, _lib
+        self.GF = gb.GF(self.field_order, **self.field_kw)
+        self.eb = self.GF._elem_bytes(self.np_dtype)
+        self.bytes_per_unit = (2 if self.op in ("inv", "neg") else 3) * self.eb
+        type(self).bytes_per_unit = self.bytes_per_unit
+        g = torch.Generator(device="cuda").manual_seed(99 + rank)
+        order = self.GF.order
+
+        def rand(low):
+            if self.eb == 16:
+                t = torch.randint(-(2**63), 2**63 - 1, (self.n, 2), dtype=torch.int64, device="cuda", generator=g)
+                t[:, 0] |= 1  # never zero
+                return t
+            tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[self.eb]
+            return torch.randint(low, order, (self.n,), dtype=torch.int64, device="cuda", generator=g).to(tdt)
+
+        a, b = rand(0), rand(1)
+        self.a = gb.DeviceArray(self.GF, a.view(torch.uint8).reshape(-1), (self.n,), self.np_dtype)
+        self.b = gb.DeviceArray(self.GF, b.view(torch.uint8).reshape(-1), (self.n,), self.np_dtype)
+        self.out = gb.DeviceArray.empty(self.GF, (self.n,), self.np_dtype)
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = self.n, 1, 0, 0
+        self.name = f"{self.GF.name} {self.op}, {self.n:.0e}-element {self.dtype} arrays per GPU"
+
+    def step(self):
+        L, lib, h, st = self._lib, self._lib.lib(), self.GF._handle(), self.gb.DeviceArray._stream()
+        if self.op in ("inv", "neg"):
+            code = L.GFB_INV if self.op == "inv" else L.GFB_NEG
+            rc = lib.gfb_unary(h, code, self.eb, self.b.data_ptr, self.out.data_ptr, self.n, st)
+        else:
+            code = {"add": L.GFB_ADD, "sub": L.GFB_SUB, "mul": L.GFB_MUL, "div": L.GFB_DIV}[self.op]
+            rc = lib.gfb_binary(h, code, self.eb, self.a.data_ptr, self.b.data_ptr, self.out.data_ptr, self.n, st)
+        L.check(rc, "gfb ewise")
+
+    def _oracle(self):
+        import oracle
+
+        if self.GF._is_prime_field:
+            return oracle.Field.prime(self.GF.order)
+        if self.GF.degree >= 64:
+            return oracle.Field128(self.GF.degree, int(self.GF.irreducible_poly))
+        return oracle.Field.binary(self.GF.degree, int(self.GF.irreducible_poly),
+                                   alpha=int(self.GF.primitive_element) if self.GF.degree <= 16 else None)
+
+    def _host(self, arr, k):
+        raw = arr.tensor[: k * self.eb].cpu().numpy()
+        if self.eb == 16:
+            return raw.view(np.uint64).reshape(-1, 2)
+        return raw.view(self.np_dtype).astype(np.int64)
+
+    def check(self):
+        import oracle
+
+        k = min(self.n, 20000 if self.eb == 16 and self.op == "inv" else 100_000)
+        if self.eb == 16 and self.op == "inv":
+            k = 300
+        a, b, got = self._host(self.a, k), self._host(self.b, k), self._host(self.out, k)
+        F = self._oracle()
+        opc = {"add": oracle.ADD, "sub": oracle.SUB, "mul": oracle.MUL, "div": oracle.DIV}
+        want = F.unary_op(oracle.INV if self.op == "inv" else oracle.NEG, b, threads=8) if self.op in ("inv", "neg") \
+            else F.binary_op(opc[self.op], a, b, threads=8)
+        assert np.array_equal(got, want), f"GPU {self.name} differs from the oracle"
+
+    def e2e_setup(self):
+        if self.eb == 16:
+            self.e2e_units = None  # object-dtype host arrays: conversion cost dominates, not a transfer benchmark
+            return
+        self.hx = self.GF.Random(self.n, seed=1, dtype=self.np_dtype)
+        self.hy = self.GF.Random(self.n, seed=2, low=1, dtype=self.np_dtype)
+        nin = 1 if self.op in ("inv", "neg") else 2
+        self.h2d, self.d2h = nin * self.eb * self.n, self.eb * self.n
+
+    def e2e_step(self):
+        if self.op == "inv":
+            self.hz = np.reciprocal(self.hy)
+        elif self.op == "neg":
+            self.hz = -self.hy
+        else:
+            self.hz = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.true_divide}[self.op](self.hx, self.hy)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        if not hasattr(self, "cF"):
+            self.cF = self._oracle() if hasattr(self, "GF") else None
+        n = self.cpu_n * threads if self.cpu_per_thread else self.cpu_n
+        if not hasattr(self, "ca"):
+            rng = np.random.default_rng(1)
+            if self.eb_cpu == 16:
+                self.ca = rng.integers(0, 2**64, (n, 2), dtype=np.uint64) | np.uint64(1)
+                self.cb = rng.integers(0, 2**64, (n, 2), dtype=np.uint64) | np.uint64(1)
+            else:
+                self.ca = rng.integers(0, self.field_order, n, dtype=np.int64)
+                self.cb = rng.integers(1, self.field_order, n, dtype=np.int64)
+        opc = {"add": oracle.ADD, "sub": oracle.SUB, "mul": oracle.MUL, "div": oracle.DIV}
+        if self.op in ("inv", "neg"):
+            self.cF.unary_op(oracle.INV if self.op == "inv" else oracle.NEG, self.cb, threads=threads)
+        else:
+            self.cF.binary_op(opc[self.op], self.ca, self.cb, threads=threads)
+        return n
+
+    cpu_n, cpu_per_thread, eb_cpu = 10**7, False, 8
+    cpu_sample = "1e7-element int64 arrays through the reference's scalar kernel (int64 DUFunc semantics), elements over OpenMP threads"
+    kernel = "k_binary / k_unary"
+
+
+def _ewise(name, **kw):
+    kw.setdefault("metric", name + "_per_sec")
+    return type("Ewise_" + name, (Ewise,), kw)
+
+
+GCM = {"irreducible_poly": "x^128 + x^7 + x^2 + x + 1", "primitive_element": 2, "verify": False}
+EWISE = {
+    "gfp_add": _ewise("gfp_add", op="add", kernel="k_binary<u64, PrimeMersenne31, ADD>"),
+    "gfp_inv": _ewise("gfp_inv", op="inv", kernel="k_unary<u64, PrimeMersenne31, INV> (batch inversion)"),
+    "gfp_div": _ewise("gfp_div", op="div", kernel="k_binary<u64, PrimeMersenne31, DIV> (batch inversion)"),
+    "gfp_mul_u32": _ewise("gfp_mul_u32", op="mul", np_dtype=np.uint32, dtype="uint32",
+                          kernel="k_binary<u32, PrimeMersenne31, MUL>"),
+    "gfp_mul_barrett": _ewise("gfp_mul_barrett", op="mul", field_order=P_NTT, np_dtype=np.uint32, dtype="uint32",
+                              kernel="k_binary<u32, PrimeBarrett, MUL>"),
+    "gf256_mul": _ewise("gf256_mul", op="mul", field_order=2**8, np_dtype=np.uint8, dtype="u8",
+                        kernel="k_binary<u8, BinaryLut, MUL>"),
+    "gf256_mul_1e6": _ewise("gf256_mul_1e6", op="mul", field_order=2**8, np_dtype=np.uint8, dtype="u8", n=10**6,
+                            kernel="k_binary<u8, BinaryLut, MUL>", cpu_n=10**6),
+    "gf2_32_mul": _ewise("gf2_32_mul", op="mul", field_order=2**32, np_dtype=np.uint32, dtype="uint32", n=10**7,
+                         kernel="k_binary<u32, BinaryCalc, MUL>", cpu_n=10**6),
+    "gf2_128_inv": _ewise("gf2_128_inv", op="inv", field_order=2**128, field_kw=GCM, np_dtype=np.object_, dtype="u128",
+                          n=10**6, kernel="k_unary<u128, Binary128, INV>", cpu_n=200, cpu_per_thread=True, eb_cpu=16),
+}
+
 WORKLOADS = {"gfp_mul": GfpMul, "ntt": Ntt, "rs_decode": RsDecode, "gf2_128_mul": Gf128Mul}
+WORKLOADS.update(EWISE)
+
+
+class RsDecodeErasures(RsDecode):
+    """RS(255,223) decode with 32 erasures per codeword (the correctable reading of BASELINE's "32 errors")."""
+
+    n_err, n_era = 0, 32
+    metric = "rs255_223_decode_erasures_cw_per_sec"
+
+
+class RsEncode(RsDecode):
+    """RS(255,223) systematic encode of 1e6 messages."""
+
+    metric, kernel, bytes_per_unit = "rs255_223_encode_cw_per_sec", "k_rs_encode", 478
+
+    def __init__(self, rank, world, total=10**6):
+        import galois_b200 as gb
+        from galois_b200._dist import shard_bounds
+
+        self.gb = gb
+        self.rs = gb.ReedSolomon(255, 223)
+        lo, hi = shard_bounds(total, rank, world)
+        self.N = hi - lo
+        self.name = f"RS(255,223) encode, {total} messages sharded over {world} GPU(s)"
+        self.M = self.rs.field.Random((self.N, 223), seed=6 + rank)
+        self.dM = self.M.to_device()
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = self.N, 1, 0, 0
+
+    def step(self):
+        self.dC = self.rs.encode_device(self.dM)
+
+    def check(self):
+        import oracle
+
+        ors = oracle.ReedSolomon(oracle.Field.binary(8, 0x11D, alpha=2), 255, 223)
+        got = self.dC.tensor[: 255 * 2000].cpu().numpy().reshape(2000, 255)
+        assert np.array_equal(got, ors.encode(np.asarray(self.M)[:2000], threads=8)), "GPU RS encode differs from the oracle"
+
+    def e2e_setup(self):
+        self.h2d, self.d2h, self.e2e_units = 223 * self.N, 255 * self.N, self.N
+
+    def e2e_step(self):
+        self.hz = self.rs.encode(self.M)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        n = 2000 * threads
+        if not hasattr(self, "ors"):
+            self.ors = oracle.ReedSolomon(oracle.Field.binary(8, 0x11D, alpha=2), 255, 223)
+            self.cM = np.random.default_rng(6).integers(0, 256, (n, 223), dtype=np.int64)
+        self.ors.encode(self.cM, threads=threads)
+        return n
+
+    cpu_sample = "2000 messages per thread (message @ P over GF(2^8) lookups, _linear.py:270-284), messages over OpenMP threads"
+
+
+class Intt(Ntt):
+    """Inverse transform of BASELINE configs[2] (scaled by 1/N)."""
+
+    metric = "intt_2p20_per_sec"
+
+    def step(self):
+        self.gb.ntt_device(self.x, inverse=True, out=self.out)
+
+    def check(self):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        p = P_NTT
+        omega = pow(int(self.GF.primitive_root_of_unity(self.N)), -1, p)
+        row = self.x.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        got = self.out.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, F.fft(row, omega, scale=pow(self.N % p, -1, p))), "GPU INTT differs from the oracle"
+
+    def e2e_step(self):
+        self.hz = self.gb.intt(self.hx)
+
+
+WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode, "intt": Intt})
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -453,12 +686,17 @@ def run_reference(args):
         return 0
     cls = WORKLOADS[args.workload]
     work = cls.__new__(cls)  # CPU leg only: no CUDA objects are created
-    if cls is Ntt:
+    if issubclass(cls, Ewise):
+        import galois_b200 as gb
+
+        work.GF = gb.GF(cls.field_order, **cls.field_kw)  # host-side description of the field only
+        work.name = f"{work.GF.name} {cls.op}"
+    if issubclass(cls, Ntt):
         import galois_b200 as gb
 
         work.GF = gb.GF(P_NTT)  # host-side constants only (omega)
     threads = cpu_threads()
-    if cls is RsDecode:
+    if cls in (RsDecode, RsDecodeErasures):
         # the CPU leg needs received words: build them with the oracle itself
         import oracle
 
@@ -467,10 +705,13 @@ def run_reference(args):
         rng = np.random.default_rng(7)
         n = 250 * threads
         C = work.ors.encode(rng.integers(0, 256, (n, 223)), threads=threads)
+        cE = np.zeros((n, 255), dtype=np.uint8)
         for i in range(n):
-            pos = rng.choice(255, 16, replace=False)
-            C[i, pos] ^= rng.integers(1, 256, 16)
+            pos = rng.choice(255, cls.n_err + cls.n_era, replace=False)
+            C[i, pos] ^= rng.integers(1, 256, len(pos))
+            cE[i, pos[cls.n_err:]] = 1
         work.cR = C
+        work.cE = cE if cls.n_era else None
     for _ in range(max(args.warmup, 1)):
         work.cpu_step(threads)
     t0 = time.perf_counter()
@@ -483,7 +724,7 @@ def run_reference(args):
         "impl": "reference", "metric": cls.metric, "value": value, "unit": cls.unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": cls.scaling, "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
-        "config": {"workload": getattr(cls, "name", cls.__doc__.strip().split("\n")[0].rstrip(".")),
+        "config": {"workload": getattr(work, "name", None) or getattr(cls, "name", None) or (cls.__doc__ or cls.__name__).strip().split("\n")[0].rstrip("."),
                    "note": "CPU oracle port of the reference path (oracle/gf_oracle.c); each step is a bounded sample"},
         "cpu_baseline": {"value": value, "unit": cls.unit, "cores": threads, "kind": "port", "sample": cls.cpu_sample},
         "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -516,9 +757,9 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     cls = WORKLOADS[args.workload]
     kw = {}
-    if args.batch is not None and cls is Ntt:
+    if args.batch is not None and issubclass(cls, Ntt):
         kw["batch"] = args.batch
-    if args.batch is not None and cls is RsDecode:
+    if args.batch is not None and issubclass(cls, RsDecode):
         kw["total"] = args.batch
     work = cls(rank, world, **kw)
 

@@ -201,42 +201,35 @@ __device__ __forceinline__ void radix32(uint32_t (&v)[32], const Mod<LAZY>& md, 
 constexpr int kRowStride = 1058;  // uint32 words per shared-memory row (1024 + 32 pad + 2: see file header)
 __device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
 
-// 1024-point NTT of one shared-memory row by one warp: X[k] left in natural order at row[padi(k)].
-// Values on exit are in [0, 4p) (LAZY) or [0, p).
-template <bool LAZY>
-__device__ __forceinline__ void warp_ntt1024(uint32_t* row, const Mod<LAZY>& md, const Radix32Roots& rt,
-                                             const uint2* __restrict__ zt) {
-    const int t = threadIdx.x & 31;
-    uint32_t v[32];
-    // round A: i = 32*i1 + i0, i0 = t; 32-point NTT over i1; then twiddle zeta^(i0*k1)
-#pragma unroll
-    for (int a = 0; a < 32; ++a) v[brev5(a)] = row[t + 33 * a];
-    radix32<LAZY>(v, md, rt);
-#pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-        if (k1 == 0) {
-            row[t] = v[0];
-        } else {
-            const uint2 z = __ldg(&zt[k1 * 32 + t]);
-            row[t + 33 * k1] = md.mul(v[k1], z.x, z.y);
-        }
-    }
-    __syncwarp();
-    // round B: k1 = t; 32-point NTT over i0 (contiguous rows 32*k1 + i0); output k = k1 + 32*k0
-#pragma unroll
-    for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
-    __syncwarp();
-    radix32<LAZY>(v, md, rt);
-#pragma unroll
-    for (int k0 = 0; k0 < 32; ++k0) row[t + 33 * k0] = v[k0];
-    __syncwarp();
-}
+// ---- 1024-point NTT of 16 vectors held in one shared-memory tile -------------------------------
+// Thread mapping: w = tid & 15 selects the vector (a tile row), tq = tid >> 4 (0..15) and the
+// sub-transform index s in {0,1} select t = tq + 16 s; the two half-warps therefore work on adjacent t.
+// Vector w lives at tile[w*kRowStride + padi(j)], j in [0,1024): with kRowStride = 2 (mod 32) and one
+// pad word per 32 elements, every access below is bank-conflict free:
+//   round A  (j = t + 32 a, lanes (w, t|t+1))  -> bank 2w + t + a     (even / odd halves)
+//   round B  (j = b + 32 t, lanes (w, t|t+1))  -> bank 2w + b + t
+//   row-wise (j = 32 consecutive, fixed w)     -> 32 consecutive words
+// n = 1024 = 32 x 32:  X[k1 + 32 k0] = sum_{i0} rho^(i0 k0) zeta^(i0 k1) sum_{i1} x[32 i1 + i0] rho^(i1 k1).
 
 constexpr int kFastThreads = 256;
 constexpr int kTileW = 16;
 constexpr size_t kFastSmem = (size_t)kTileW * kRowStride * sizeof(uint32_t);
 
-// pass 1: column NTTs + four-step twiddle.  One CTA per (transform, 16-column tile).
+// second half of round A: twiddle by zeta^(t k1) and park Y[k1] at j = t + 32 k1
+template <bool LAZY>
+__device__ __forceinline__ void round_a_store(uint32_t* row, int t, const uint32_t (&v)[32], const Mod<LAZY>& md,
+                                              const uint2* __restrict__ zt) {
+    row[t] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) {
+        const uint2 z = __ldg(&zt[k1 * 32 + t]);
+        row[t + 33 * k1] = md.mul(v[k1], z.x, z.y);
+    }
+}
+
+// pass 1: column NTTs + four-step twiddle.  One CTA per (transform, 16-column tile).  Lanes run along the 16
+// columns, so the strided global reads (64 B segments) go straight into registers and the results go straight
+// from registers to the workspace: the tile is only used for the exchange between the two radix-32 rounds.
 template <typename T, bool LAZY, int OCC>
 __global__ void __launch_bounds__(kFastThreads, OCC)
     k_ntt_pass1(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint2* __restrict__ tw4,
@@ -244,31 +237,47 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
     extern __shared__ uint32_t tile[];
     const size_t transform = blockIdx.x >> 6;
     const int c0 = (blockIdx.x & 63) * kTileW;
-    const T* src = x + (transform << 20) + c0;
-    uint32_t* dst = ws + (transform << 20) + c0;
-#pragma unroll 16
-    for (int it = 0; it < 64; ++it) {
-        const int e = it * kFastThreads + threadIdx.x;
-        const int w = e & 15, r = e >> 4;
-        tile[w * kRowStride + padi(r)] = (uint32_t)src[(size_t)r * 1024 + w];
+    const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    const T* src = x + (transform << 20) + c0 + w;
+    uint32_t* dst = ws + (transform << 20) + c0 + w;
+    const uint2* twc = tw4 + c0 + w;
+    uint32_t* row = tile + w * kRowStride;
+    uint32_t v[32];
+    {
+        // x[(32 a + t) * 1024 + c]: element i1 = a of the sub-transform i0 = t.  Both sub-transforms' loads
+        // (64 independent 4-byte loads per thread) are issued before any arithmetic: one DRAM latency per CTA.
+        uint32_t u[32];
+#pragma unroll
+        for (int a = 0; a < 32; ++a) v[brev5(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq) * 1024);
+#pragma unroll
+        for (int a = 0; a < 32; ++a) u[brev5(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq + 16) * 1024);
+        radix32<LAZY>(v, md, rt);
+        round_a_store<LAZY>(row, tq, v, md, zt);
+        radix32<LAZY>(u, md, rt);
+        round_a_store<LAZY>(row, tq + 16, u, md, zt);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    warp_ntt1024<LAZY>(tile + (warp * 2) * kRowStride, md, rt, zt);
-    warp_ntt1024<LAZY>(tile + (warp * 2 + 1) * kRowStride, md, rt, zt);
-    __syncthreads();
-#pragma unroll 8
-    for (int it = 0; it < 64; ++it) {
-        const int e = it * kFastThreads + threadIdx.x;
-        const int w = e & 15, k = e >> 4;
-        const uint2 tw = __ldg(&tw4[(size_t)k * 1024 + c0 + w]);
-        uint32_t val = md.mul(tile[w * kRowStride + padi(k)], tw.x, tw.y);
-        if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
-        dst[(size_t)k * 1024 + w] = val;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int t = tq + 16 * s;  // k1
+#pragma unroll
+        for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
+        radix32<LAZY>(v, md, rt);
+        // k = k1 + 32 k0; multiply by scale * omega^(c k) and store ws[k][c]
+#pragma unroll
+        for (int k0 = 0; k0 < 32; ++k0) {
+            const size_t k = (size_t)(t + 32 * k0);
+            const uint2 tw = __ldg(twc + k * 1024);
+            uint32_t val = md.mul(v[k0], tw.x, tw.y);
+            if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
+            dst[k * 1024] = val;
+        }
     }
 }
 
-// pass 2: row NTTs + transposed store.  One CTA per (transform, 16-row tile).
+// pass 2: row NTTs + transposed store.  One CTA per (transform, 16-row tile).  The 16 rows are contiguous in
+// the workspace, so they are staged through the tile (coalesced along the row, transposed by the tile layout);
+// the outputs X[k1 + 1024 k2] have the 16 rows (k1) innermost and go straight from registers to global memory.
 template <typename T, bool LAZY, int OCC>
 __global__ void __launch_bounds__(kFastThreads, OCC)
     k_ntt_pass2(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint32_t* __restrict__ ws,
@@ -277,23 +286,43 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
     const size_t transform = blockIdx.x >> 6;
     const int k1_0 = (blockIdx.x & 63) * kTileW;
     const uint32_t* src = ws + (transform << 20) + (size_t)k1_0 * 1024;
-    T* dst = y + (transform << 20) + k1_0;
-#pragma unroll 16
-    for (int it = 0; it < 64; ++it) {
-        const int e = it * kFastThreads + threadIdx.x;
-        const int i = e & 1023, w = e >> 10;
-        tile[w * kRowStride + padi(i)] = src[(size_t)w * 1024 + i];
+    const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    T* dst = y + (transform << 20) + k1_0 + w;
+    // 16 rows x 1024 contiguous words = 4096 uint4: 16 per thread, consecutive threads consecutive uint4
+    {
+        const uint4* src4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int e = it * kFastThreads + threadIdx.x;  // uint4 index within the tile
+            const int ww = e >> 8, i = (e & 255) * 4;
+            const uint4 q = __ldg(src4 + e);
+            uint32_t* d = tile + ww * kRowStride + padi(i);  // i % 4 == 0: the four words share one pad offset
+            d[0] = q.x;
+            d[1] = q.y;
+            d[2] = q.z;
+            d[3] = q.w;
+        }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    warp_ntt1024<LAZY>(tile + (warp * 2) * kRowStride, md, rt, zt);
-    warp_ntt1024<LAZY>(tile + (warp * 2 + 1) * kRowStride, md, rt, zt);
+    uint32_t* row = tile + w * kRowStride;
+    uint32_t v[32];
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int t = tq + 16 * s;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) v[brev5(a)] = row[t + 33 * a];
+        radix32<LAZY>(v, md, rt);
+        round_a_store<LAZY>(row, t, v, md, zt);  // in place: thread (w, t) owns positions {t + 32 a}
+    }
     __syncthreads();
-#pragma unroll 8
-    for (int it = 0; it < 64; ++it) {
-        const int e = it * kFastThreads + threadIdx.x;
-        const int w = e & 15, k2 = e >> 4;
-        dst[(size_t)k2 * 1024 + w] = (T)md.canon(tile[w * kRowStride + padi(k2)]);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int t = tq + 16 * s;  // k1 of the inner transform
+#pragma unroll
+        for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
+        radix32<LAZY>(v, md, rt);
+#pragma unroll
+        for (int k0 = 0; k0 < 32; ++k0) dst[(size_t)(t + 32 * k0) * 1024] = (T)md.canon(v[k0]);
     }
 }
 
