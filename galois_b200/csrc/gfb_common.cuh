@@ -55,6 +55,8 @@ struct PrimeBarrett {
     static constexpr bool kNeedsSmem = false;
     uint32_t p;
     unsigned long long mu;  // floor(2^64 / p)
+    uint32_t pinv;          // p^-1 mod 2^32 (odd p), for Montgomery reduction
+    uint32_t r2;            // 2^64 mod p
 
     __device__ __forceinline__ void init_smem(void*) const {}
     __device__ __forceinline__ elem zero() const { return 0u; }
@@ -79,8 +81,20 @@ struct PrimeBarrett {
         if (r >= p) r -= p;
         return (uint32_t)r;
     }
+    // a * b * 2^-32 mod p for a, b < p (p odd): Montgomery reduction, 3 multiplies
+    __device__ __forceinline__ elem montmul(elem a, elem b) const {
+        const unsigned long long t = (unsigned long long)a * (unsigned long long)b;
+        const uint32_t m = (uint32_t)t * pinv;
+        const uint32_t u = __umulhi(m, p);
+        const uint32_t hi = (uint32_t)(t >> 32);
+        uint32_t r = hi - u;  // t - m*p is divisible by 2^32: the low words cancel exactly
+        if (hi < u) r += p;
+        return r;
+    }
     __device__ __forceinline__ elem mul(elem a, elem b) const {
-        return reduce64((unsigned long long)a * (unsigned long long)b);
+        // two Montgomery steps: (a b 2^-32) (2^64) 2^-32 = a b.  ~12 integer instructions instead of a 64-bit Barrett.
+        if (p == 2u) return a & b;
+        return montmul(montmul(a, b), r2);
     }
     // order - 1 as an unsigned 64-bit integer (exponent modulus)
     __device__ __forceinline__ unsigned long long group_order() const { return (unsigned long long)p - 1ull; }
@@ -237,14 +251,60 @@ struct BinaryLut {
 };
 
 // ----------------------------------------------------------------------------------------
-// GF(2^m), 64 < m <= 128 on two limbs.
+// Carry-less multiplication without a CLMUL instruction: operands are split into four bit-slices
+// (bits = i mod 4) so that the integer multiplier's carries land in the three-zero gaps; each slice
+// has at most 8 set bits, so a column sum is at most 8 and never reaches the next slice position.
+// 16 IMAD.WIDE + ~30 logic operations per 32x32 -> 64 bit product.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long clmul32(uint32_t x, uint32_t y) {
+    const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+    const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+#define GFB_M(a, b) ((unsigned long long)(a) * (unsigned long long)(b))
+    unsigned long long z0 = GFB_M(x0, y0) ^ GFB_M(x1, y3) ^ GFB_M(x2, y2) ^ GFB_M(x3, y1);
+    unsigned long long z1 = GFB_M(x0, y1) ^ GFB_M(x1, y0) ^ GFB_M(x2, y3) ^ GFB_M(x3, y2);
+    unsigned long long z2 = GFB_M(x0, y2) ^ GFB_M(x1, y1) ^ GFB_M(x2, y0) ^ GFB_M(x3, y3);
+    unsigned long long z3 = GFB_M(x0, y3) ^ GFB_M(x1, y2) ^ GFB_M(x2, y1) ^ GFB_M(x3, y0);
+#undef GFB_M
+    return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) |
+           (z3 & 0x8888888888888888ull);
+}
+
+// 64 x 64 -> 128 (Karatsuba over 32-bit halves: 3 clmul32)
+__device__ __forceinline__ void clmul64(unsigned long long a, unsigned long long b, unsigned long long& lo,
+                                        unsigned long long& hi) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const unsigned long long p0 = clmul32(a0, b0), p2 = clmul32(a1, b1);
+    const unsigned long long p1 = clmul32(a0 ^ a1, b0 ^ b1) ^ p0 ^ p2;
+    lo = p0 ^ (p1 << 32);
+    hi = p2 ^ (p1 >> 32);
+}
+
+// spread the 32 bits of x to the even bit positions of a 64-bit word (squaring in GF(2)[x])
+__device__ __forceinline__ unsigned long long spread32(uint32_t x) {
+    unsigned long long v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// GF(2^m), 64 <= m <= 128 on two 64-bit limbs.  Multiply = 128x128 Karatsuba (9 clmul32) followed by
+// folding the high part with the low-degree tail r(x) of the irreducible polynomial x^m + r(x).
+// Inverse = Itoh-Tsujii addition chain on 2^(m-1) - 1 (about log2(m) + popcount(m-1) multiplies and
+// m - 1 squarings) instead of the reference's plain square-and-multiply of a^(2^m - 2)
+// (_calculate.py:470-489) — the inverse is unique, so the result is the same element.
 // ----------------------------------------------------------------------------------------
 struct Binary128 {
     using elem = u128;
     static constexpr bool kNeedsSmem = false;
     int m;
-    u128 poly_low;  // irreducible polynomial without the x^m term
+    u128 poly_low;  // r(x): irreducible polynomial without the x^m term
     u128 mask;      // 2^m - 1
+    int n_shift;    // > 0: r(x) = sum x^shift[i] with every shift < 64 (sparse tail, e.g. GCM's x^7+x^2+x+1)
+    unsigned char shift[8];
 
     __device__ __forceinline__ void init_smem(void*) const {}
     __device__ __forceinline__ elem zero() const { return u128{0ull, 0ull}; }
@@ -253,35 +313,81 @@ struct Binary128 {
     __device__ __forceinline__ elem add(elem a, elem b) const { return u128{a.lo ^ b.lo, a.hi ^ b.hi}; }
     __device__ __forceinline__ elem sub(elem a, elem b) const { return add(a, b); }
     __device__ __forceinline__ elem neg(elem a) const { return a; }
-    __device__ __forceinline__ elem xtime(elem a) const {
-        // a * x mod poly
-        const int top = m - 1;
-        unsigned long long carry = top >= 64 ? (a.hi >> (top - 64)) & 1ull : (a.lo >> top) & 1ull;
-        elem r;
-        r.hi = ((a.hi << 1) | (a.lo >> 63)) & mask.hi;
-        r.lo = (a.lo << 1) & mask.lo;
-        // branch-free conditional xor
-        unsigned long long sel = 0ull - carry;
-        r.lo ^= poly_low.lo & sel;
-        r.hi ^= poly_low.hi & sel;
-        return r;
+
+    // 128 x 128 -> 256 bits, c[0] least significant
+    static __device__ __forceinline__ void mul256(const u128& a, const u128& b, unsigned long long (&c)[4]) {
+        unsigned long long p0, p1, q0, q1, m0, m1;
+        clmul64(a.lo, b.lo, p0, p1);
+        clmul64(a.hi, b.hi, q0, q1);
+        clmul64(a.lo ^ a.hi, b.lo ^ b.hi, m0, m1);
+        m0 ^= p0 ^ q0;
+        m1 ^= p1 ^ q1;
+        c[0] = p0;
+        c[1] = p1 ^ m0;
+        c[2] = q0 ^ m1;
+        c[3] = q1;
     }
-    __device__ __forceinline__ elem mul(elem a, elem b) const {
-        elem c = zero();
+
+    // c (256 bits) mod x^m + r(x)
+    __device__ __forceinline__ elem reduce(unsigned long long (&c)[4]) const {
+        const int sh = m - 64;  // 0..64
 #pragma unroll 1
-        for (int limb = 0; limb < 2; ++limb) {
-            unsigned long long w = limb ? b.hi : b.lo;
-            if (limb == 1 && w == 0ull) break;
-#pragma unroll 4
-            for (int i = 0; i < 64; ++i) {
-                unsigned long long sel = 0ull - (w & 1ull);
-                c.lo ^= a.lo & sel;
-                c.hi ^= a.hi & sel;
-                w >>= 1;
-                a = xtime(a);
+        for (int guard = 0; guard < 256; ++guard) {
+            // H = c >> m  (at most 128 bits), L = c mod x^m
+            unsigned long long h0, h1;
+            if (sh == 0) {
+                h0 = c[1];
+                h1 = c[2];
+            } else if (sh == 64) {
+                h0 = c[2];
+                h1 = c[3];
+            } else {
+                h0 = (c[1] >> sh) | (c[2] << (64 - sh));
+                h1 = (c[2] >> sh) | (c[3] << (64 - sh));
+            }
+            if ((h0 | h1) == 0ull) break;
+            const u128 L{c[0] & mask.lo, c[1] & mask.hi};
+            if (n_shift > 0) {
+                unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull;
+                for (int i = 0; i < n_shift; ++i) {
+                    const int s = shift[i];
+                    if (s == 0) {
+                        t0 ^= h0;
+                        t1 ^= h1;
+                    } else {
+                        t0 ^= h0 << s;
+                        t1 ^= (h1 << s) | (h0 >> (64 - s));
+                        t2 ^= h1 >> (64 - s);
+                    }
+                }
+                c[0] = L.lo ^ t0;
+                c[1] = L.hi ^ t1;
+                c[2] = t2;
+                c[3] = 0ull;
+            } else {
+                unsigned long long t[4];
+                mul256(u128{h0, h1}, poly_low, t);
+                c[0] = L.lo ^ t[0];
+                c[1] = L.hi ^ t[1];
+                c[2] = t[2];
+                c[3] = t[3];
             }
         }
-        return c;
+        return u128{c[0] & mask.lo, c[1] & mask.hi};
+    }
+
+    __device__ __forceinline__ elem mul(elem a, elem b) const {
+        unsigned long long c[4];
+        mul256(a, b, c);
+        return reduce(c);
+    }
+    __device__ __forceinline__ elem sqr(elem a) const {
+        unsigned long long c[4];
+        c[0] = spread32((uint32_t)a.lo);
+        c[1] = spread32((uint32_t)(a.lo >> 32));
+        c[2] = spread32((uint32_t)a.hi);
+        c[3] = spread32((uint32_t)(a.hi >> 32));
+        return reduce(c);
     }
     __device__ __forceinline__ unsigned long long group_order() const { return ~0ull; }  // not used (> 2^64)
     __device__ __forceinline__ elem pow_u64(elem a, unsigned long long e) const {
@@ -289,17 +395,29 @@ struct Binary128 {
         while (e) {
             if (e & 1ull) r = mul(r, a);
             e >>= 1;
-            if (e) a = mul(a, a);
+            if (e) a = sqr(a);
         }
         return r;
     }
+    // a^-1 = (a^(2^(m-1) - 1))^2 with beta_k = a^(2^k - 1):  beta_2k = beta_k^(2^k) * beta_k,  beta_(k+1) = beta_k^2 * a
     __device__ __forceinline__ elem inv1(elem a) const {
-        elem t = a, r = one();
-        for (int i = 1; i < m; ++i) {
-            t = mul(t, t);
-            r = mul(r, t);
+        const int e = m - 1;
+        int top = 31 - __clz(e);
+        elem beta = a;
+        int k = 1;
+#pragma unroll 1
+        for (int bit = top - 1; bit >= 0; --bit) {
+            elem t = beta;
+#pragma unroll 1
+            for (int i = 0; i < k; ++i) t = sqr(t);
+            beta = mul(t, beta);
+            k <<= 1;
+            if ((e >> bit) & 1) {
+                beta = mul(sqr(beta), a);
+                k += 1;
+            }
         }
-        return r;
+        return sqr(beta);
     }
 };
 
@@ -354,9 +472,10 @@ struct gfb_field {
     uint64_t order_lo;       // p, or 2^m when m < 64 (0 otherwise)
     uint64_t poly_lo, poly_hi;
     uint64_t primitive_element;
-    // Barrett
+    // Barrett / Montgomery constants
     uint32_t p;
     unsigned long long mu;
+    uint32_t pinv, r2;
     // lookup tables (m <= 16 built on host; staged in smem when m <= 12)
     uint16_t* d_exp;
     uint16_t* d_log;
@@ -366,7 +485,7 @@ struct gfb_field {
     int* h_err;
     int* d_err;
 
-    gfb::PrimeBarrett prime_barrett() const { return gfb::PrimeBarrett{p, mu}; }
+    gfb::PrimeBarrett prime_barrett() const { return gfb::PrimeBarrett{p, mu, pinv, r2}; }
     gfb::PrimeMersenne31 prime_m31() const { return gfb::PrimeMersenne31{}; }
     gfb::BinaryCalc bin_calc() const {
         unsigned long long mask = degree == 64 ? ~0ull : ((1ull << degree) - 1ull);
@@ -383,6 +502,12 @@ struct gfb_field {
             mask = gfb::u128{~0ull, (1ull << (degree - 64)) - 1ull};
         }
         pl = gfb::u128{poly_lo & mask.lo, poly_hi & mask.hi};
-        return gfb::Binary128{degree, pl, mask};
+        gfb::Binary128 b{degree, pl, mask, 0, {0, 0, 0, 0, 0, 0, 0, 0}};
+        // sparse low-degree tail: fold the high half with a few shifts instead of another 128x128 product
+        if (pl.hi == 0ull && __builtin_popcountll(pl.lo) <= 8) {
+            for (int i = 0; i < 64; ++i)
+                if ((pl.lo >> i) & 1ull) b.shift[b.n_shift++] = (unsigned char)i;
+        }
+        return b;
     }
 };

@@ -15,7 +15,13 @@
 namespace gfb {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnrollDefault = 4;
+// 128-bit vectors in flight per thread and operand: 4 for the word-size fields (memory-bound, wants MLP);
+// 2 for the 16-byte GF(2^m) elements, whose carry-less multiply is register-hungry and ALU-bound.
+template <typename T>
+struct UnrollFor {
+    static constexpr int value = sizeof(T) == 16 ? 2 : kUnrollDefault;
+};
 
 enum Mode { MODE_AA = 0, MODE_AS = 1, MODE_SA = 2 };  // array∘array, array∘scalar, scalar∘array
 
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) k_binary(F f, const T* __restrict__ 
             s = f.inv1(s);
         }
     }
+    constexpr int kUnroll = UnrollFor<T>::value;
     const size_t nvec = n / VEC;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,6 +225,8 @@ __global__ void __launch_bounds__(kThreads) k_unary(F f, const T* __restrict__ a
     extern __shared__ uint4 smem_raw[];
     f.init_smem(smem_raw);
     bool zero_seen = false;
+    // inversion amortises one field inverse over the K elements a thread holds: keep 4 vectors there
+    constexpr int kUnroll = (OP == GFB_INV) ? kUnrollDefault : UnrollFor<T>::value;
     const size_t nvec = n / VEC;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,11 +364,11 @@ static gfb_status launch_binary_t(F f, const void* a, const void* b, typename F:
     const bool fast = aligned16(a) && aligned16(out) && (MODE != MODE_AA || aligned16(b));
     const size_t smem = smem_for(f);
     if (fast) {
-        size_t items = (n / VEC + kUnroll - 1) / kUnroll + (n % VEC) + 1;
+        size_t items = (n / VEC + kUnrollDefault - 1) / kUnrollDefault + (n % VEC) + 1;
         int grid = grid_for(items, 16);
         k_binary<T, F, OP, MODE, VEC><<<grid, kThreads, smem, st>>>(f, (const T*)a, (const T*)b, s, (T*)out, n, err);
     } else {
-        size_t items = (n + kUnroll - 1) / kUnroll + 1;
+        size_t items = (n + kUnrollDefault - 1) / kUnrollDefault + 1;
         int grid = grid_for(items, 16);
         k_binary<T, F, OP, MODE, 1><<<grid, kThreads, smem, st>>>(f, (const T*)a, (const T*)b, s, (T*)out, n, err);
     }
@@ -446,10 +455,10 @@ static gfb_status launch_unary_t(F f, const void* a, void* out, size_t n, int* e
     const bool fast = aligned16(a) && aligned16(out);
     const size_t smem = smem_for(f);
     if (fast) {
-        size_t items = (n / VEC + kUnroll - 1) / kUnroll + (n % VEC) + 1;
+        size_t items = (n / VEC + kUnrollDefault - 1) / kUnrollDefault + (n % VEC) + 1;
         k_unary<T, F, OP, VEC><<<grid_for(items, 16), kThreads, smem, st>>>(f, (const T*)a, (T*)out, n, err);
     } else {
-        size_t items = (n + kUnroll - 1) / kUnroll + 1;
+        size_t items = (n + kUnrollDefault - 1) / kUnrollDefault + 1;
         k_unary<T, F, OP, 1><<<grid_for(items, 16), kThreads, smem, st>>>(f, (const T*)a, (T*)out, n, err);
     }
     GFB_CUDA_TRY(cudaGetLastError());

@@ -97,6 +97,11 @@ gfb_status gfb_field_create(gfb_field** out, int kind, uint64_t order_lo, int de
         unsigned __int128 one = (unsigned __int128)1 << 64;
         f->mu = (unsigned long long)(one / order_lo);
         if (order_lo == 2) f->mu = 0x8000000000000000ull;  // exact 2^63
+        // Montgomery constants: p^-1 mod 2^32 by Newton iteration (odd p), 2^64 mod p
+        uint32_t inv = f->p;  // correct to 3 bits
+        for (int i = 0; i < 5; ++i) inv *= 2u - f->p * inv;
+        f->pinv = inv;
+        f->r2 = (uint32_t)(one % order_lo);
         f->impl = (order_lo == 0x7fffffffull) ? gfb::IMPL_PRIME_M31 : gfb::IMPL_PRIME_BARRETT;
     } else if (kind == GFB_BINARY) {
         if (degree < 1 || degree > 128) {
