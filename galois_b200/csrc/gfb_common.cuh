@@ -256,10 +256,16 @@ struct BinaryLut {
 // has at most 8 set bits, so a column sum is at most 8 and never reaches the next slice position.
 // 16 IMAD.WIDE + ~30 logic operations per 32x32 -> 64 bit product.
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mul_wide_u32(uint32_t a, uint32_t b) {
+    unsigned long long r;  // one IMAD.WIDE.U32 (the C++ form leaves dead 64x64 cross-term adds behind)
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 __device__ __forceinline__ unsigned long long clmul32(uint32_t x, uint32_t y) {
     const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
     const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
-#define GFB_M(a, b) ((unsigned long long)(a) * (unsigned long long)(b))
+#define GFB_M(a, b) mul_wide_u32(a, b)
     unsigned long long z0 = GFB_M(x0, y0) ^ GFB_M(x1, y3) ^ GFB_M(x2, y2) ^ GFB_M(x3, y1);
     unsigned long long z1 = GFB_M(x0, y1) ^ GFB_M(x1, y0) ^ GFB_M(x2, y3) ^ GFB_M(x3, y2);
     unsigned long long z2 = GFB_M(x0, y2) ^ GFB_M(x1, y1) ^ GFB_M(x2, y0) ^ GFB_M(x3, y3);

@@ -17,10 +17,11 @@ namespace gfb {
 constexpr int kThreads = 256;
 constexpr int kUnrollDefault = 4;
 // 128-bit vectors in flight per thread and operand: 4 for the word-size fields (memory-bound, wants MLP);
-// 2 for the 16-byte GF(2^m) elements, whose carry-less multiply is register-hungry and ALU-bound.
+// 1 for the 16-byte GF(2^m) elements, whose carry-less multiply is register-hungry and ALU-bound (occupancy matters more).
 template <typename T>
 struct UnrollFor {
-    static constexpr int value = sizeof(T) == 16 ? 2 : kUnrollDefault;
+    static constexpr int value = sizeof(T) == 16 ? 1 : kUnrollDefault;
+    static constexpr int min_blocks = sizeof(T) == 16 ? 3 : 1;  // register cap for the ALU-bound 16-byte fields
 };
 
 enum Mode { MODE_AA = 0, MODE_AS = 1, MODE_SA = 2 };  // array∘array, array∘scalar, scalar∘array
@@ -109,7 +110,7 @@ __device__ __forceinline__ void apply_binary(const F& f, typename F::elem (&a)[K
 
 // VEC = elements per thread-load: 16/sizeof(T) (aligned fast path) or 1 (unaligned fallback).
 template <typename T, typename F, int OP, int MODE, int VEC>
-__global__ void __launch_bounds__(kThreads) k_binary(F f, const T* __restrict__ a, const T* __restrict__ b,
+__global__ void __launch_bounds__(kThreads, OP == GFB_DIV ? 1 : UnrollFor<T>::min_blocks) k_binary(F f, const T* __restrict__ a, const T* __restrict__ b,
                                                       typename F::elem s, T* __restrict__ out, size_t n, int* err) {
     using E = typename F::elem;
     extern __shared__ uint4 smem_raw[];
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(kThreads) k_binary(F f, const T* __restrict__ 
             s = f.inv1(s);
         }
     }
-    constexpr int kUnroll = UnrollFor<T>::value;
+    // division carries a batch inversion: keep 4 vectors per thread there to amortise the field inverse
+    constexpr int kUnroll = (OP == GFB_DIV) ? kUnrollDefault : UnrollFor<T>::value;
     const size_t nvec = n / VEC;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +221,7 @@ __device__ __forceinline__ void apply_unary(const F& f, typename F::elem (&a)[K]
 }
 
 template <typename T, typename F, int OP, int VEC>
-__global__ void __launch_bounds__(kThreads) k_unary(F f, const T* __restrict__ a, T* __restrict__ out, size_t n,
+__global__ void __launch_bounds__(kThreads, OP == GFB_INV ? 1 : UnrollFor<T>::min_blocks) k_unary(F f, const T* __restrict__ a, T* __restrict__ out, size_t n,
                                                      int* err) {
     using E = typename F::elem;
     extern __shared__ uint4 smem_raw[];
