@@ -156,13 +156,61 @@ struct PrimeMersenne31 {
 };
 
 // ----------------------------------------------------------------------------------------
-// Binary extension fields GF(2^m), 1 <= m <= 64, explicit calculation.  Compute type uint64_t.
+// Carry-less multiplication without a CLMUL instruction: operands are split into four bit-slices
+// (bits = i mod 4) so that the integer multiplier's carries land in the three-zero gaps; each slice
+// has at most 8 set bits, so a column sum is at most 8 and never reaches the next slice position.
+// 16 IMAD.WIDE + ~30 logic operations per 32x32 -> 64 bit product.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mul_wide_u32(uint32_t a, uint32_t b) {
+    unsigned long long r;  // one IMAD.WIDE.U32 (the C++ form leaves dead 64x64 cross-term adds behind)
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long clmul32(uint32_t x, uint32_t y) {
+    const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+    const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+#define GFB_M(a, b) mul_wide_u32(a, b)
+    unsigned long long z0 = GFB_M(x0, y0) ^ GFB_M(x1, y3) ^ GFB_M(x2, y2) ^ GFB_M(x3, y1);
+    unsigned long long z1 = GFB_M(x0, y1) ^ GFB_M(x1, y0) ^ GFB_M(x2, y3) ^ GFB_M(x3, y2);
+    unsigned long long z2 = GFB_M(x0, y2) ^ GFB_M(x1, y1) ^ GFB_M(x2, y0) ^ GFB_M(x3, y3);
+    unsigned long long z3 = GFB_M(x0, y3) ^ GFB_M(x1, y2) ^ GFB_M(x2, y1) ^ GFB_M(x3, y0);
+#undef GFB_M
+    return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) |
+           (z3 & 0x8888888888888888ull);
+}
+
+// 64 x 64 -> 128 (Karatsuba over 32-bit halves: 3 clmul32)
+__device__ __forceinline__ void clmul64(unsigned long long a, unsigned long long b, unsigned long long& lo,
+                                        unsigned long long& hi) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const unsigned long long p0 = clmul32(a0, b0), p2 = clmul32(a1, b1);
+    const unsigned long long p1 = clmul32(a0 ^ a1, b0 ^ b1) ^ p0 ^ p2;
+    lo = p0 ^ (p1 << 32);
+    hi = p2 ^ (p1 >> 32);
+}
+
+// spread the 32 bits of x to the even bit positions of a 64-bit word (squaring in GF(2)[x])
+__device__ __forceinline__ unsigned long long spread32(uint32_t x) {
+    unsigned long long v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// Binary extension fields GF(2^m), 1 <= m <= 63, explicit calculation.  Compute type uint64_t.
+// The product is the same element the reference's shift-and-xor loop yields (_calculate.py:309-324):
+// full carry-less product, then the part above x^m is folded back with r(x) = poly - x^m.
 // ----------------------------------------------------------------------------------------
 struct BinaryCalc {
     using elem = unsigned long long;
     static constexpr bool kNeedsSmem = false;
     int m;
-    unsigned long long poly_low;  // irreducible polynomial WITHOUT the x^m term
+    unsigned long long poly_low;  // r(x): irreducible polynomial WITHOUT the x^m term
     unsigned long long mask;      // 2^m - 1
 
     __device__ __forceinline__ void init_smem(void*) const {}
@@ -172,17 +220,38 @@ struct BinaryCalc {
     __device__ __forceinline__ elem add(elem a, elem b) const { return a ^ b; }
     __device__ __forceinline__ elem sub(elem a, elem b) const { return a ^ b; }
     __device__ __forceinline__ elem neg(elem a) const { return a; }
-    __device__ __forceinline__ elem mul(elem a, elem b) const {
-        elem c = 0ull;
-        const int top = m - 1;
-        while (b) {
-            if (b & 1ull) c ^= a;
-            b >>= 1;
-            unsigned long long carry = (a >> top) & 1ull;
-            a = (a << 1) & mask;
-            if (carry) a ^= poly_low;
+    // (c1:c0) mod x^m + r(x); the degree drops by m - deg r >= 1 per fold
+    __device__ __forceinline__ elem reduce(unsigned long long c0, unsigned long long c1) const {
+        if (m <= 32) {
+            // c1 == 0 and every intermediate fits 64 bits
+#pragma unroll 1
+            for (int guard = 0; guard < 64; ++guard) {
+                const unsigned long long h = c0 >> m;
+                if (h == 0ull) break;
+                c0 = (c0 & mask) ^ clmul32((uint32_t)h, (uint32_t)poly_low);
+            }
+            return c0;
         }
-        return c;
+#pragma unroll 1
+        for (int guard = 0; guard < 128; ++guard) {
+            const unsigned long long h = (c0 >> m) | (c1 << (64 - m));  // c has < 2m bits: h fits 64 bits
+            if (h == 0ull) break;
+            unsigned long long t0, t1;
+            clmul64(h, poly_low, t0, t1);
+            c0 = (c0 & mask) ^ t0;
+            c1 = t1;
+        }
+        return c0 & mask;
+    }
+    __device__ __forceinline__ elem mul(elem a, elem b) const {
+        if (m <= 32) return reduce(clmul32((uint32_t)a, (uint32_t)b), 0ull);
+        unsigned long long c0, c1;
+        clmul64(a, b, c0, c1);
+        return reduce(c0, c1);
+    }
+    __device__ __forceinline__ elem sqr(elem a) const {
+        if (m <= 32) return reduce(spread32((uint32_t)a), 0ull);
+        return reduce(spread32((uint32_t)a), spread32((uint32_t)(a >> 32)));
     }
     __device__ __forceinline__ unsigned long long group_order() const { return mask; }  // 2^m - 1
     __device__ __forceinline__ elem pow_u64(elem a, unsigned long long e) const {
@@ -190,18 +259,30 @@ struct BinaryCalc {
         while (e) {
             if (e & 1ull) r = mul(r, a);
             e >>= 1;
-            if (e) a = mul(a, a);
+            if (e) a = sqr(a);
         }
         return r;
     }
+    // a^-1 = (a^(2^(m-1) - 1))^2, Itoh-Tsujii chain (see Binary128::inv1)
     __device__ __forceinline__ elem inv1(elem a) const {
-        // a^(2^m - 2) = prod_{i=1}^{m-1} a^(2^i)
-        elem t = a, r = 1ull;
-        for (int i = 1; i < m; ++i) {
-            t = mul(t, t);
-            r = mul(r, t);
+        if (m == 1) return a;
+        const int e = m - 1;
+        const int top = 31 - __clz(e);
+        elem beta = a;
+        int k = 1;
+#pragma unroll 1
+        for (int bit = top - 1; bit >= 0; --bit) {
+            elem t = beta;
+#pragma unroll 1
+            for (int i = 0; i < k; ++i) t = sqr(t);
+            beta = mul(t, beta);
+            k <<= 1;
+            if ((e >> bit) & 1) {
+                beta = mul(sqr(beta), a);
+                k += 1;
+            }
         }
-        return r;
+        return sqr(beta);
     }
 };
 
@@ -249,52 +330,6 @@ struct BinaryLut {
     }
     __device__ __forceinline__ elem inv1(elem a) const { return s_exp[(order - 1u) - (uint32_t)s_log[a]]; }
 };
-
-// ----------------------------------------------------------------------------------------
-// Carry-less multiplication without a CLMUL instruction: operands are split into four bit-slices
-// (bits = i mod 4) so that the integer multiplier's carries land in the three-zero gaps; each slice
-// has at most 8 set bits, so a column sum is at most 8 and never reaches the next slice position.
-// 16 IMAD.WIDE + ~30 logic operations per 32x32 -> 64 bit product.
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long mul_wide_u32(uint32_t a, uint32_t b) {
-    unsigned long long r;  // one IMAD.WIDE.U32 (the C++ form leaves dead 64x64 cross-term adds behind)
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
-    return r;
-}
-
-__device__ __forceinline__ unsigned long long clmul32(uint32_t x, uint32_t y) {
-    const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
-    const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
-#define GFB_M(a, b) mul_wide_u32(a, b)
-    unsigned long long z0 = GFB_M(x0, y0) ^ GFB_M(x1, y3) ^ GFB_M(x2, y2) ^ GFB_M(x3, y1);
-    unsigned long long z1 = GFB_M(x0, y1) ^ GFB_M(x1, y0) ^ GFB_M(x2, y3) ^ GFB_M(x3, y2);
-    unsigned long long z2 = GFB_M(x0, y2) ^ GFB_M(x1, y1) ^ GFB_M(x2, y0) ^ GFB_M(x3, y3);
-    unsigned long long z3 = GFB_M(x0, y3) ^ GFB_M(x1, y2) ^ GFB_M(x2, y1) ^ GFB_M(x3, y0);
-#undef GFB_M
-    return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) |
-           (z3 & 0x8888888888888888ull);
-}
-
-// 64 x 64 -> 128 (Karatsuba over 32-bit halves: 3 clmul32)
-__device__ __forceinline__ void clmul64(unsigned long long a, unsigned long long b, unsigned long long& lo,
-                                        unsigned long long& hi) {
-    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    const unsigned long long p0 = clmul32(a0, b0), p2 = clmul32(a1, b1);
-    const unsigned long long p1 = clmul32(a0 ^ a1, b0 ^ b1) ^ p0 ^ p2;
-    lo = p0 ^ (p1 << 32);
-    hi = p2 ^ (p1 >> 32);
-}
-
-// spread the 32 bits of x to the even bit positions of a 64-bit word (squaring in GF(2)[x])
-__device__ __forceinline__ unsigned long long spread32(uint32_t x) {
-    unsigned long long v = x;
-    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
-    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
-    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
-    v = (v | (v << 2)) & 0x3333333333333333ull;
-    v = (v | (v << 1)) & 0x5555555555555555ull;
-    return v;
-}
 
 // ----------------------------------------------------------------------------------------
 // GF(2^m), 64 <= m <= 128 on two 64-bit limbs.  Multiply = 128x128 Karatsuba (9 clmul32) followed by
