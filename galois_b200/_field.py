@@ -108,6 +108,8 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
             return x
         if isinstance(x, (list, tuple)):
             x = np.array(x, dtype=object if cls._wide else None)
+            if x.size == 0:
+                x = x.astype(dtype)  # np.array([]) is float64; an empty field array is fine
         if isinstance(x, np.ndarray):
             if x.dtype == np.object_:
                 flat = [int(v) for v in x.ravel()]
