@@ -39,7 +39,7 @@ namespace gfb {
 constexpr int kRsWarps = 8;
 constexpr int kRsThreads = kRsWarps * 32;
 constexpr int kMaxN = 256;
-constexpr int kScratchArrays = 14;
+constexpr int kScratchArrays = 18;  // 14 byte arrays + 2 uint16 arrays of kMaxN entries
 
 struct RsDev {
     int n, k, d, c, q1, log_alpha, order;
@@ -110,12 +110,17 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_encode(RsDev rs, const uint8_
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
+// Branch-free GF(2^m) arithmetic on shared-memory tables: LOG[0] = kLogZero and EXP[i] = 0 for i >= kLogZero, so a
+// zero operand needs no test (EXP is kExpSize bytes: the largest index is 2 * kLogZero).
+constexpr int kLogZero = 512;
+constexpr int kExpSize = 2 * kLogZero + 4;
+
 struct Gf8 {
     const uint8_t* e;
-    const uint8_t* l;
+    const uint16_t* l;
     int q1;
     __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) const {
-        return (a && b) ? e[(uint32_t)l[a] + (uint32_t)l[b]] : 0u;
+        return e[(uint32_t)l[a] + (uint32_t)l[b]];
     }
     __device__ __forceinline__ uint32_t inv(uint32_t a) const { return e[q1 - l[a]]; }
     // alpha^x for any integer x, given log(alpha)
@@ -137,17 +142,17 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                                                            uint8_t* __restrict__ decoded, long long* __restrict__ n_errors,
                                                            size_t N) {
     extern __shared__ uint8_t smem[];
-    uint8_t* s_exp = smem;
-    uint8_t* s_log = s_exp + 2 * rs.order;
-    uint8_t* s_scratch = s_log + rs.order;
-    for (int i = threadIdx.x; i < 2 * rs.order; i += blockDim.x) s_exp[i] = rs.exp8[i];
-    for (int i = threadIdx.x; i < rs.order; i += blockDim.x) s_log[i] = rs.log8[i];
+    uint8_t* s_exp = smem;                                              // kExpSize
+    uint16_t* s_log = reinterpret_cast<uint16_t*>(smem + kExpSize);     // 256 entries
+    uint8_t* s_scratch = smem + kExpSize + 256 * sizeof(uint16_t);
+    for (int i = threadIdx.x; i < kExpSize; i += blockDim.x) s_exp[i] = i < 2 * rs.order ? rs.exp8[i] : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_log[i] = (i > 0 && i < rs.order) ? rs.log8[i] : kLogZero;
     __syncthreads();
     const Gf8 gf{s_exp, s_log, rs.q1};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* w = s_scratch + (size_t)warp * kScratchArrays * kMaxN;
     uint8_t* rec = w + 0 * kMaxN;      // received, ascending degree, erasures zeroed
-    uint8_t* rlog = w + 1 * kMaxN;     // LOG(rec) or 255
+    uint16_t* rlog = reinterpret_cast<uint16_t*>(w + 14 * kMaxN);  // LOG(rec), kLogZero for a zero symbol
     uint8_t* epos = w + 2 * kMaxN;     // erasure positions (ascending degree index)
     uint8_t* S = w + 3 * kMaxN;        // syndromes
     uint8_t* gam = w + 4 * kMaxN;      // Γ, ascending
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
     uint8_t* Om = w + 10 * kMaxN;      // Ω'
     uint8_t* pos = w + 11 * kMaxN;     // error/erasure positions found by the Chien search
     uint8_t* lam = w + 12 * kMaxN;     // Λ, ascending
-    uint8_t* tmp = w + 13 * kMaxN;
+    uint16_t* tmp = reinterpret_cast<uint16_t*>(w + 16 * kMaxN);  // LOG(Λ_total)
     const int d1 = rs.d - 1;
     const int la = rs.log_alpha;
     const int q1 = rs.q1;
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
             u += __popc(bal);
             if (i < ns) {
                 rec[i] = (uint8_t)v;
-                rlog[i] = v ? s_log[v] : 255;
+                rlog[i] = s_log[v];
             }
         }
         __syncwarp();
@@ -206,11 +211,11 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                 const int lr = (int)(((long long)la * (rs.c + l)) % q1);  // log of the root
                 int e = 0;                                                // lr * i mod q1 for i = 0
                 uint32_t acc = 0;
+#pragma unroll 4
                 for (int i = 0; i < ns; ++i) {
-                    const uint32_t lg = rlog[i];
-                    if (lg != 255u) acc ^= s_exp[lg + (uint32_t)e];
+                    acc ^= s_exp[(uint32_t)rlog[i] + (uint32_t)e];  // zero symbols land in EXP's zero region
                     e += lr;
-                    if (e >= q1) e -= q1;
+                    e = min((uint32_t)e, (uint32_t)(e - q1));  // e mod q1 without a compare (e < 2 q1)
                 }
                 S[l] = (uint8_t)acc;
                 any_nz |= acc;
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                 const int i1 = j < u ? j : u;
                 for (int i = i0; i <= i1; ++i) acc ^= gf.mul(gam[i], lam[j - i]);
                 Lt[j] = (uint8_t)acc;
-                tmp[j] = acc ? s_log[acc] : 255;  // log Λ_total
+                tmp[j] = s_log[acc];  // log Λ_total
             }
             __syncwarp();
             // ---- 6. Chien search over i = 0..design_n-1: Λ_total(alpha^-i) == 0 (:1464-1475)
@@ -327,11 +332,11 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                     lx = lx ? q1 - lx : 0;
                     int e = 0;
                     val = 0;
+#pragma unroll 4
                     for (int j = 0; j < lt_len; ++j) {
-                        const uint32_t lg = tmp[j];
-                        if (lg != 255u) val ^= s_exp[lg + (uint32_t)e];
+                        val ^= s_exp[(uint32_t)tmp[j] + (uint32_t)e];
                         e += lx;
-                        if (e >= q1) e -= q1;
+                        e = min((uint32_t)e, (uint32_t)(e - q1));
                     }
                 }
                 const bool root = (i < ns) && (val == 0);  // roots at i >= n are not recorded (:1469-1472)
@@ -520,7 +525,7 @@ gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t
     if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
     if (N == 0) return GFB_OK;
     RsDev d = make_dev(rs);
-    const size_t smem = 3 * (size_t)d.order + (size_t)kRsWarps * kScratchArrays * kMaxN;
+    const size_t smem = kExpSize + 256 * sizeof(uint16_t) + (size_t)kRsWarps * kScratchArrays * kMaxN;
     GFB_CUDA_TRY(cudaFuncSetAttribute(k_rs_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_rs_decode<<<rs_grid(N), kRsThreads, smem, (cudaStream_t)stream>>>(d, received, erasures, ns, decoded,
                                                                          (long long*)n_errors, N);
