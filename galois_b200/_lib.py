@@ -59,6 +59,7 @@ SIGNATURES = {
     "gfb_matmul": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int, _vp]),
     "gfb_matmul_host": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int]),
     "gfb_rs_create": (_int, [C.POINTER(_vp), _vp, _int, _int, _int, _u64]),
+    "gfb_bch_create": (_int, [C.POINTER(_vp), _vp, _int, _int, _int, _int, _u64, _vp]),
     "gfb_rs_destroy": (None, [_vp]),
     "gfb_rs_get_generator_poly": (_int, [_vp, _vp]),
     "gfb_rs_get_parity_matrix": (_int, [_vp, _vp]),

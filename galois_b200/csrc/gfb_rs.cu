@@ -24,7 +24,8 @@
 
 struct gfb_rs_code {
     gfb_field* field;
-    int n, k, d, c, m;
+    int n, k, d, c, m;  // d = design distance: d - 1 consecutive roots alpha^c .. alpha^(c+d-2)
+    int base2;      // 1: symbols live in the prime subfield GF(2) (binary BCH), 0: in the field itself (RS)
     int q1;         // order - 1
     int log_alpha;  // alpha = EXP[log_alpha]
     std::vector<uint8_t> gen;   // d coefficients, degree-descending
@@ -42,7 +43,7 @@ constexpr int kMaxN = 256;
 constexpr int kScratchArrays = 18;  // 14 byte arrays + 2 uint16 arrays of kMaxN entries
 
 struct RsDev {
-    int n, k, d, c, q1, log_alpha, order;
+    int n, k, d, c, q1, log_alpha, order, base2;
     const uint8_t* exp8;
     const uint8_t* log8;
     const uint8_t* logP;
@@ -380,8 +381,16 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                         if (ex < 0) ex += q1;
                         E = gf.mul(E, s_exp[ex]);
                     }
-                    // ---- 10. correct (:1567-1576)
-                    rec[i] ^= (uint8_t)E;
+                    // ---- 10. correct (:1567-1576): c_hat = SUBTRACT_BASE(r, E).  For RS the base field is the field itself
+                    //      (xor).  For binary BCH it is GF(2), whose subtract_modular (_calculate.py:245-251) is
+                    //      `a - b if a >= b else 2 + a - b` on int64, cast back to uint8: identical to xor for E in
+                    //      {0, 1}, and reproduced literally for the (miscorrected) E > 1 cases.
+                    if (rs.base2) {
+                        const int a = rec[i], b = (int)E;
+                        rec[i] = (uint8_t)(a >= b ? a - b : 2 + a - b);
+                    } else {
+                        rec[i] ^= (uint8_t)E;
+                    }
                 }
                 __syncwarp();
                 for (int i = lane; i < ns; i += 32) drow[ns - 1 - i] = rec[i];
@@ -398,6 +407,7 @@ static RsDev make_dev(const gfb_rs_code* rs) {
     d.k = rs->k;
     d.d = rs->d;
     d.c = rs->c;
+    d.base2 = rs->base2;
     d.q1 = rs->q1;
     d.log_alpha = rs->log_alpha;
     d.order = rs->q1 + 1;
@@ -418,41 +428,34 @@ static int rs_grid(size_t N) {
 
 extern "C" {
 
-gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha) {
+// Shared builder: a cyclic code of length n over GF(2^m) symbols (or GF(2) symbols embedded in it) with generator
+// polynomial `gen` (n-k+1 coefficients, degree-descending) and d-1 consecutive roots alpha^c .. alpha^(c+d-2).
+static gfb_status code_create(gfb_rs_code** out, gfb_field* f, int n, int k, int d, int c, uint64_t alpha,
+                              const uint8_t* gen, int base2) {
     using namespace gfb;
-    if (!out) return GFB_ERR_BAD_ARG;
-    *out = nullptr;
-    if (!f || f->kind != GFB_BINARY) return GFB_ERR_BAD_ARG;
-    if (f->degree > 8 || !f->h_exp) return GFB_ERR_UNSUPPORTED;
     const int order = 1 << f->degree;
     const int q1 = order - 1;
-    if (n < 1 || n > q1 || k < 1 || k > n || c < 0 || (q1 % n) != 0) return GFB_ERR_BAD_ARG;
-    if (alpha == 0 || alpha >= (uint64_t)order) return GFB_ERR_BAD_ARG;
     gfb_rs_code* rs = new gfb_rs_code();
     rs->field = f;
     rs->n = n;
     rs->k = k;
-    rs->d = n - k + 1;
+    rs->d = d;
     rs->c = c;
     rs->m = f->degree;
+    rs->base2 = base2;
     rs->q1 = q1;
     rs->log_alpha = f->h_log[alpha];
     rs->d_exp8 = rs->d_log8 = rs->d_logP = nullptr;
     HostGf gf{f->h_exp, f->h_log, q1};
     const int r = n - k;
-    // g(x) = prod_{i=0}^{d-2} (x - alpha^(c+i)), degree-descending (_reed_solomon.py:206-207)
-    rs->gen.assign(rs->d, 0);
-    rs->gen[0] = 1;
-    int len = 1;
-    for (int i = 0; i < rs->d - 1; ++i) {
-        uint8_t root = gf.pow_alpha(rs->log_alpha, c + i);
-        rs->gen[len] = 0;
-        for (int j = len; j >= 1; --j) rs->gen[j] ^= gf.mul(rs->gen[j - 1], root);
-        len += 1;
-    }
+    rs->gen.assign(gen, gen + r + 1);
     // systematic parity block P (_codes/_cyclic.py:206-217)
     rs->P.assign((size_t)k * (r > 0 ? r : 1), 0);
     if (r > 0) {
+        if (rs->gen[r] == 0 || rs->gen[0] == 0) {
+            delete rs;
+            return GFB_ERR_BAD_ARG;
+        }
         const uint8_t g_last_inv = gf.inv(rs->gen[r]);
         for (int j = 0; j < r; ++j) rs->P[j] = gf.mul(rs->gen[j], g_last_inv);
         for (int i = 1; i < k; ++i) {
@@ -476,12 +479,54 @@ gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, u
     if (e == cudaSuccess) e = cudaMemcpy(rs->d_log8, log8.data(), log8.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(rs->d_logP, logP.data(), logP.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-        set_last_error("gfb_rs_create upload", e);
+        set_last_error("code_create upload", e);
         gfb_rs_destroy(rs);
         return GFB_ERR_CUDA;
     }
     *out = rs;
     return GFB_OK;
+}
+
+static gfb_status code_args_ok(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha) {
+    if (!out) return GFB_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!f || f->kind != GFB_BINARY) return GFB_ERR_BAD_ARG;
+    if (f->degree > 8 || !f->h_exp) return GFB_ERR_UNSUPPORTED;
+    const int order = 1 << f->degree;
+    const int q1 = order - 1;
+    if (n < 1 || n > q1 || k < 1 || k > n || c < 0 || (q1 % n) != 0) return GFB_ERR_BAD_ARG;
+    if (alpha == 0 || alpha >= (uint64_t)order) return GFB_ERR_BAD_ARG;
+    return GFB_OK;
+}
+
+gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha) {
+    using namespace gfb;
+    gfb_status st = code_args_ok(out, f, n, k, c, alpha);
+    if (st != GFB_OK) return st;
+    HostGf gf{f->h_exp, f->h_log, (1 << f->degree) - 1};
+    const int d = n - k + 1;
+    // g(x) = prod_{i=0}^{d-2} (x - alpha^(c+i)), degree-descending (_reed_solomon.py:206-207)
+    std::vector<uint8_t> gen(d, 0);
+    gen[0] = 1;
+    int len = 1;
+    const int la = f->h_log[alpha];
+    for (int i = 0; i < d - 1; ++i) {
+        uint8_t root = gf.pow_alpha(la, c + i);
+        gen[len] = 0;
+        for (int j = len; j >= 1; --j) gen[j] ^= gf.mul(gen[j - 1], root);
+        len += 1;
+    }
+    return code_create(out, f, n, k, d, c, alpha, gen.data(), 0);
+}
+
+gfb_status gfb_bch_create(gfb_rs_code** out, gfb_field* extension_field, int n, int k, int d, int c, uint64_t alpha,
+                          const uint8_t* generator_poly) {
+    gfb_status st = code_args_ok(out, extension_field, n, k, c, alpha);
+    if (st != GFB_OK) return st;
+    if (!generator_poly || d < 1 || d - 1 > n - k) return GFB_ERR_BAD_ARG;
+    for (int i = 0; i <= n - k; ++i)
+        if (generator_poly[i] > 1) return GFB_ERR_BAD_ARG;  // binary BCH: g(x) has coefficients in GF(2)
+    return code_create(out, extension_field, n, k, d, c, alpha, generator_poly, 1);
 }
 
 void gfb_rs_destroy(gfb_rs_code* rs) {
@@ -494,7 +539,7 @@ void gfb_rs_destroy(gfb_rs_code* rs) {
 
 gfb_status gfb_rs_get_generator_poly(const gfb_rs_code* rs, uint8_t* g) {
     if (!rs || !g) return GFB_ERR_BAD_ARG;
-    memcpy(g, rs->gen.data(), rs->d);
+    memcpy(g, rs->gen.data(), rs->gen.size());
     return GFB_OK;
 }
 

@@ -169,6 +169,13 @@ gfb_status gfb_matmul_host(gfb_field* f, int elem_bytes, const void* A, const vo
  * _poly_to_generator_matrix (_codes/_cyclic.py:198-226, systematic) for codes over
  * GF(2^m), m <= 8: generator roots alpha^c .. alpha^(c+d-2), d = n-k+1. */
 gfb_status gfb_rs_create(gfb_rs_code** out, gfb_field* f, int n, int k, int c, uint64_t alpha);
+/* Binary BCH(n, k) with design distance d over GF(2), syndromes in extension_field = GF(2^m), m <= 8: replaces
+ * BCH.__init__ (_codes/_bch.py:184-240).  `generator_poly` holds the n-k+1 coefficients (0/1, degree-descending)
+ * of g(x) = lcm of the minimal polynomials of alpha^c .. alpha^(c+d-2) (_bch.py:1178-1197), computed by the
+ * caller; the returned handle is used with the gfb_rs_* encode / decode / get_* entry points (the reference
+ * shares one decoder between both code families, _reed_solomon.py:1105-1113).  Symbols are bytes 0/1. */
+gfb_status gfb_bch_create(gfb_rs_code** out, gfb_field* extension_field, int n, int k, int d, int c,
+                          uint64_t alpha, const uint8_t* generator_poly);
 void gfb_rs_destroy(gfb_rs_code* rs);
 /* Copies of the code's constants (host memory, caller-allocated):
  *   generator_poly: n-k+1 coefficients, degree-descending;  parity: k x (n-k) matrix P of G=[I|P]. */

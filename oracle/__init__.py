@@ -388,3 +388,106 @@ class Field128:
 def prime_mul_i64(p: int, a: np.ndarray, b: np.ndarray, out: np.ndarray, threads: int = 1) -> None:
     """The reference's int64 GF(p) multiply loop, for the CPU baseline (no allocation)."""
     lib().orc_prime_mul_i64(ctypes.c_int64(p), _ptr(a), _ptr(b), _ptr(out), ctypes.c_int64(a.size), threads)
+
+
+# ------------------------------------------------------------------------ binary BCH (SURVEY.md §8f.1)
+def _gf2m_mul(a: int, b: int, m: int, poly: int) -> int:
+    """multiply_binary.calculate, _domains/_calculate.py:309-324 (pure Python; cold path)."""
+    c, order = 0, 1 << m
+    while b:
+        if b & 1:
+            c ^= a
+        b >>= 1
+        a <<= 1
+        if a >= order:
+            a ^= poly
+    return c
+
+
+def _gf2m_pow(a: int, e: int, m: int, poly: int) -> int:
+    r = 1
+    while e:
+        if e & 1:
+            r = _gf2m_mul(r, a, m, poly)
+        a = _gf2m_mul(a, a, m, poly)
+        e >>= 1
+    return r
+
+
+def _gf2_polymul(a: int, b: int) -> int:
+    r = 0
+    while b:
+        if b & 1:
+            r ^= a
+        a <<= 1
+        b >>= 1
+    return r
+
+
+def bch_generator_poly(m: int, poly: int, d: int, alpha: int, c: int):
+    """_generator_poly_from_d, _codes/_bch.py:1178-1197, for field = GF(2): g(x) as a GF(2)[x] bit mask and the
+    d-1 roots alpha^(c+i).  The minimal polynomial of a root is prod (x - root^(2^j)) over its conjugates."""
+    g, roots, seen = 1, [], []
+    for i in range(d - 1):
+        root = _gf2m_pow(alpha, c + i, m, poly)
+        roots.append(root)
+        conj, b = [], root
+        while b not in conj:
+            conj.append(b)
+            b = _gf2m_mul(b, b, m, poly)
+        coeffs = [1]
+        for cj in conj:
+            nxt = [0] * (len(coeffs) + 1)
+            for j, a in enumerate(coeffs):
+                nxt[j + 1] ^= a
+                nxt[j] ^= _gf2m_mul(a, cj, m, poly)
+            coeffs = nxt
+        assert all(v in (0, 1) for v in coeffs)
+        mi = sum(v << j for j, v in enumerate(coeffs))
+        if mi not in seen:
+            g = _gf2_polymul(g, mi)
+            seen.append(mi)
+    return g, roots
+
+
+class BCH:
+    """Binary BCH(n, k, d): symbols in GF(2), decoding arithmetic in ``ext`` = GF(2^m) (a lookup ``Field``).
+    Encode is the systematic product over GF(2) (_linear.py:270-284), decode is bch_decode_jit with
+    field = GF(2), extension_field = GF(2^m) (_bch.py:721-727, 1337-1578)."""
+
+    def __init__(self, ext: Field, n: int, d: int, c: int = 1, alpha: int = 2):
+        self.ext, self.n, self.d, self.c, self.alpha = ext, n, d, c, alpha
+        g, roots = bch_generator_poly(ext.m, ext.poly, d, alpha, c)
+        r = g.bit_length() - 1
+        self.k = n - r
+        self.generator_poly = np.array([(g >> (r - i)) & 1 for i in range(r + 1)], dtype=np.int64)
+        self.roots = np.array(roots, dtype=np.int64)
+        self.base = Field.prime(2)
+        self.P = np.zeros((self.k, max(r, 1)), dtype=np.int64)
+        if r:
+            lib().orc_rs_parity_matrix(self.base.ref, n, self.k, _ptr(self.generator_poly), _ptr(self.P))
+        self.P = self.P[:, :r]
+
+    def encode(self, msg, threads: int = 1) -> np.ndarray:
+        msg = np.atleast_2d(_i64(msg))
+        N, ks = msg.shape
+        cw = np.empty((N, ks + self.n - self.k), dtype=np.int64)
+        P = np.ascontiguousarray(self.P)
+        lib().orc_rs_encode(self.base.ref, self.n, self.k, _ptr(P), _ptr(msg), ks, _ptr(cw), ctypes.c_int64(N), threads)
+        return cw
+
+    def decode(self, codewords, erasures=None, threads: int = 1):
+        cw = np.atleast_2d(_i64(codewords))
+        N, ns = cw.shape
+        er = None
+        if erasures is not None:
+            er = np.ascontiguousarray(np.atleast_2d(np.asarray(erasures)).astype(np.uint8))
+        dec = np.empty_like(cw)
+        n_err = np.zeros(N, dtype=np.int64)
+        rc = lib().orc_bch_decode(
+            self.ext.ref, self.base.ref, _ptr(cw), _ptr(er) if er is not None else None, ctypes.c_int64(N), ns, self.n,
+            ctypes.c_int64(self.alpha), self.c, _ptr(self.roots), self.d, _ptr(dec), _ptr(n_err), threads)
+        if rc:
+            raise ValueError("oracle bch_decode: bad arguments")
+        # dec_codeword.astype(codeword.dtype), _bch.py:1299: GF(2) arrays are uint8
+        return dec.astype(np.uint8).astype(np.int64), n_err

@@ -55,3 +55,13 @@ def live_linalg():
 @pytest.fixture(scope="session")
 def live_rs():
     return _load("live_rs.npz"), json.load(open(GOLDEN / "live_rs_meta.json"))
+
+
+@pytest.fixture(scope="session")
+def ref_bch():
+    return _load("ref_bch.npz")
+
+
+@pytest.fixture(scope="session")
+def live_bch():
+    return _load("live_bch.npz"), json.load(open(GOLDEN / "live_bch_meta.json"))

@@ -383,8 +383,106 @@ def live_rs():
     print("live_rs.npz", len(out), "arrays")
 
 
+def convert_bch_vectors():
+    """The reference's Sage vectors for binary BCH codes (tests/codes/data/bch/n15_*_sys.pkl with q = 2)."""
+    out, names = {}, []
+    folder = REF / "tests" / "codes" / "data" / "bch"
+    for f in sorted(folder.glob("*_sys.pkl")):
+        d = pickle.load(open(f, "rb"))
+        if d["q"] != 2:
+            continue
+        name = f.stem
+        names.append(name)
+        out[f"{name}/params"] = np.array([d["q"], d["n"], d["k"], d["d"], d["alpha"], d["c"]], dtype=np.int64)
+        out[f"{name}/G"] = np.asarray(d["G"], dtype=np.int64)
+        out[f"{name}/messages"] = np.asarray(d["encode"]["messages"], dtype=np.int64)
+        out[f"{name}/codewords"] = np.asarray(d["encode"]["codewords"], dtype=np.int64)
+        if d.get("encode_shortened") and "messages" in d["encode_shortened"]:
+            out[f"{name}/short_messages"] = np.asarray(d["encode_shortened"]["messages"], dtype=np.int64)
+            out[f"{name}/short_codewords"] = np.asarray(d["encode_shortened"]["codewords"], dtype=np.int64)
+    out["names"] = np.array(names)
+    np.savez_compressed(OUT / "ref_bch.npz", **out)
+    print("ref_bch.npz", len(names), "codes")
+
+
+def live_bch():
+    """Binary BCH codes on the live reference: construction (by k and by d), encode, decode under error / erasure
+    patterns including uncorrectable ones, shortened codes."""
+    out, meta = {}, {}
+    rng = np.random.default_rng(17)
+    codes = [("bch15_7", dict(n=15, k=7), 32), ("bch15_5", dict(n=15, k=5), 16), ("bch31_16", dict(n=31, k=16), 16),
+             ("bch63_36", dict(n=63, k=36), 16), ("bch127_64", dict(n=127, k=64), 8),
+             ("bch255_131", dict(n=255, k=131), 24), ("bch255_d37", dict(n=255, d=37), 8),
+             ("bch255_223_c3", dict(n=255, d=9, c=3), 8), ("bch51_27", dict(n=51, d=9, extension_field=galois.GF(2**8)), 8)]
+    GF2 = galois.GF(2)
+
+    def store(key, bch, R, E):
+        """Decode row by row: beyond the design distance the reference can miscorrect to a word with non-binary
+        symbols and then raises ValueError from `.view(GF(2))` (_bch.py:1300, _fields/_array.py:177); record that."""
+        Rn = np.asarray(R)
+        dec = Rn.astype(np.int64).copy()
+        nerr = np.zeros(Rn.shape[0], dtype=np.int64)
+        raised = np.zeros(Rn.shape[0], dtype=bool)
+        for i in range(Rn.shape[0]):
+            try:
+                d_i, n_i = bch.decode(R[i], erasures=E[i] if E is not None else None, output="codeword", errors=True)
+                dec[i], nerr[i] = np.asarray(d_i).astype(np.int64), n_i
+            except ValueError:
+                raised[i] = True
+        out[f"{key}/received"] = Rn.astype(np.int64)
+        out[f"{key}/erasures"] = E if E is not None else np.zeros(Rn.shape, dtype=bool)
+        out[f"{key}/decoded"] = dec
+        out[f"{key}/n_errors"] = nerr
+        out[f"{key}/raised"] = raised
+
+    for name, kw, N in codes:
+        bch = galois.BCH(**kw)
+        EF = bch.extension_field
+        t = (bch.d - 1) // 2
+        meta[name] = {"n": bch.n, "k": bch.k, "d": bch.d, "c": int(bch.c), "alpha": int(bch.alpha), "t": t,
+                      "m": EF.degree, "irreducible_poly": int(EF.irreducible_poly),
+                      "primitive_element": int(EF.primitive_element), "by_k": "k" in kw}
+        out[f"{name}/generator_poly"] = np.asarray(bch.generator_poly.coeffs).astype(np.int64)
+        out[f"{name}/roots"] = np.asarray(bch.roots).astype(np.int64)
+        out[f"{name}/G"] = np.asarray(bch.G).astype(np.int64)
+        M = GF2.Random((N, bch.k), seed=int(rng.integers(1 << 30)))
+        C = bch.encode(M)
+        out[f"{name}/messages"] = np.asarray(M).astype(np.int64)
+        out[f"{name}/codewords"] = np.asarray(C).astype(np.int64)
+
+        def corrupt2(C, n_err, n_era):
+            R = np.asarray(C).copy()
+            E = np.zeros(R.shape, dtype=bool)
+            for i in range(R.shape[0]):
+                pos = rng.choice(R.shape[1], n_err + n_era, replace=False)
+                R[i, pos[:n_err]] ^= 1
+                E[i, pos[n_err:]] = True
+                R[i, pos[n_err:]] = rng.integers(0, 2, n_era)
+            return GF2(R), E
+
+        patterns = {"clean": (0, 0), "t_errors": (t, 0), "one_error": (min(1, t), 0), "max_erasures": (0, bch.d - 1),
+                    "mixed": (t // 2, bch.d - 1 - 2 * (t // 2)), "t_plus_1": (t + 1, 0), "too_many": (min(bch.n, bch.d + 3), 0),
+                    "era_plus_1": (1, bch.d - 1)}
+        for pname, (ne, nu) in patterns.items():
+            if ne + nu > bch.n:
+                continue
+            R, E = corrupt2(C, ne, nu)
+            store(f"{name}/{pname}", bch, R, E if nu else None)
+        s = max(1, bch.k // 3)
+        Ms = GF2.Random((N, bch.k - s), seed=int(rng.integers(1 << 30)))
+        Cs = bch.encode(Ms)
+        out[f"{name}/short/messages"] = np.asarray(Ms).astype(np.int64)
+        out[f"{name}/short/codewords"] = np.asarray(Cs).astype(np.int64)
+        for pname, (ne, nu) in {"t_errors": (t, 0), "t_plus_1": (t + 1, 0)}.items():
+            R, E = corrupt2(Cs, ne, nu)
+            store(f"{name}/short/{pname}", bch, R, None)
+    json.dump(meta, open(OUT / "live_bch_meta.json", "w"), indent=1)
+    np.savez_compressed(OUT / "live_bch.npz", **out)
+    print("live_bch.npz", len(out), "arrays")
+
+
 def main():
-    which = sys.argv[1:] or ["fields", "rs_ref", "elementwise", "gf128", "ntt", "linalg", "rs"]
+    which = sys.argv[1:] or ["fields", "rs_ref", "elementwise", "gf128", "ntt", "linalg", "rs", "bch_ref", "bch"]
     if "fields" in which:
         convert_field_vectors()
     if "rs_ref" in which:
@@ -399,6 +497,10 @@ def main():
         live_linalg()
     if "rs" in which:
         live_rs()
+    if "bch_ref" in which:
+        convert_bch_vectors()
+    if "bch" in which:
+        live_bch()
 
 
 if __name__ == "__main__":

@@ -140,3 +140,28 @@ def test_ntt_argument_checks_need_no_gpu():
         gb.ntt([1, 2, 3, 40], modulus=43)
     with pytest.raises(ValueError):
         gb.ntt([1, 2, 3, 4], modulus=3 * 256 + 2)
+
+
+def test_bch_construction_matches_reference(live_bch):
+    """BCH.__init__ host logic (generator polynomial from d / search from k, _codes/_bch.py:1178-1252) vs the live
+    reference's codes; no GPU needed."""
+    data, meta = live_bch
+    for name, m in meta.items():
+        ext = gb.GF(2 ** m["m"], irreducible_poly=m["irreducible_poly"], primitive_element=m["primitive_element"])
+        if m["by_k"]:
+            bch = gb.BCH(m["n"], m["k"], extension_field=ext, alpha=m["alpha"], c=m["c"])
+        else:
+            bch = gb.BCH(m["n"], d=m["d"], extension_field=ext, alpha=m["alpha"], c=m["c"])
+        assert (bch.n, bch.k, bch.d, bch.t) == (m["n"], m["k"], m["d"], m["t"]), name
+        assert np.array_equal(np.asarray(bch.generator_poly), data[f"{name}/generator_poly"]), name
+        assert np.array_equal(np.asarray(bch.roots), data[f"{name}/roots"]), name
+        assert bch.field.order == 2 and bch.extension_field is ext
+    assert gb.BCH(15, 7).d == 5 and gb.BCH(15, d=5).k == 7  # default extension field GF(2^4), x^4 + x + 1
+    with pytest.raises(ValueError):
+        gb.BCH(15, 8)
+    with pytest.raises(ValueError):
+        gb.BCH(15, 7, 7)
+    with pytest.raises(ValueError):
+        gb.BCH(15)
+    with pytest.raises(NotImplementedError):
+        gb.BCH(13, 4, field=gb.GF(3))

@@ -422,3 +422,74 @@ def test_rs_255_223_bulk_vs_oracle():
     dec, nerr = rs.decode(R, output="codeword", errors=True)
     assert np.array_equal(np.asarray(dec), Ch)
     assert (nerr >= 0).all() and (nerr <= 16).all()
+
+
+def test_ref_vectors_bch_encode(ref_bch):
+    """Sage vectors for the binary BCH(15, k) codes of the reference's test-suite through the CUDA encoder."""
+    for name in ref_bch["names"]:
+        q, n, k, d, alpha, c = (int(v) for v in ref_bch[f"{name}/params"])
+        bch = gb.BCH(n, d=d, alpha=alpha, c=c)
+        assert bch.k == k
+        assert np.array_equal(np.asarray(bch.G), ref_bch[f"{name}/G"]), name
+        cw = bch.encode(ref_bch[f"{name}/messages"])
+        assert type(cw) is gb.GF(2) and np.array_equal(np.asarray(cw), ref_bch[f"{name}/codewords"]), name
+        if f"{name}/short_messages" in ref_bch.files:
+            assert np.array_equal(np.asarray(bch.encode(ref_bch[f"{name}/short_messages"])), ref_bch[f"{name}/short_codewords"])
+        if k < n:
+            assert not bch.detect(cw).any()
+
+
+def test_live_bch(live_bch):
+    """Binary BCH encode / errors-and-erasures decode vs the live reference, incl. the rows on which the reference
+    raises ValueError (miscorrection to non-binary symbols)."""
+    data, meta = live_bch
+    for name, m in meta.items():
+        ext = gb.GF(2 ** m["m"], irreducible_poly=m["irreducible_poly"], primitive_element=m["primitive_element"])
+        bch = gb.BCH(m["n"], d=m["d"], extension_field=ext, alpha=m["alpha"], c=m["c"])
+        GF2 = bch.field
+        assert np.array_equal(np.asarray(bch.G), data[f"{name}/G"]), name
+        assert np.array_equal(np.asarray(bch.encode(data[f"{name}/messages"])), data[f"{name}/codewords"]), name
+        assert np.array_equal(np.asarray(bch.encode(data[f"{name}/short/messages"])), data[f"{name}/short/codewords"])
+        pats = sorted({k[len(name) + 1:].rsplit("/", 1)[0] for k in data.files
+                       if k.startswith(name + "/") and k.endswith("/received")})
+        for pat in pats:
+            R, E = data[f"{name}/{pat}/received"], data[f"{name}/{pat}/erasures"]
+            raised = data[f"{name}/{pat}/raised"]
+            ok = ~raised
+            if ok.any():
+                dec, nerr = bch.decode(R[ok], erasures=E[ok] if E.any() else None, output="codeword", errors=True)
+                assert type(dec) is GF2 and nerr.dtype == np.int64
+                assert np.array_equal(nerr, data[f"{name}/{pat}/n_errors"][ok]), (name, pat)
+                assert np.array_equal(np.asarray(dec), data[f"{name}/{pat}/decoded"][ok]), (name, pat)
+            for i in np.flatnonzero(raised)[:3]:
+                with pytest.raises(ValueError, match="GF\\(2\\) arrays must have elements"):
+                    bch.decode(R[i], erasures=E[i] if E.any() else None)
+
+
+def test_bch_255_131_bulk_vs_oracle():
+    """BCH(255,131,t=18): 20000 codewords with 18 bit errors each vs the oracle, and a 2e5-codeword round trip."""
+    bch = gb.BCH(255, 131)
+    assert bch.d == 37
+    F = oracle.Field.binary(8, 0x11D, alpha=2)
+    ob = oracle.BCH(F, 255, 37)
+    N = 20000
+    M = bch.field.Random((N, 131), seed=1)
+    C = bch.encode(M)
+    assert np.array_equal(np.asarray(C), ob.encode(np.asarray(M), threads=8))
+    rng = np.random.default_rng(2)
+    R = np.asarray(C).copy()
+    cols = np.argsort(rng.random((N, 255)), axis=1)[:, :18]
+    R[np.arange(N)[:, None], cols] ^= 1
+    dec, nerr = bch.decode(R, output="codeword", errors=True)
+    odec, onerr = ob.decode(R, threads=8)
+    assert np.array_equal(nerr, onerr) and (nerr == 18).all()
+    assert np.array_equal(np.asarray(dec), odec) and np.array_equal(np.asarray(dec), np.asarray(C))
+    N = 200_000
+    M = bch.field.Random((N, 131), seed=3)
+    C = np.asarray(bch.encode(M))
+    R = C.copy()
+    cols = np.argsort(rng.random((N, 255)), axis=1)[:, :18]
+    R[np.arange(N)[:, None], cols] ^= 1
+    dec, nerr = bch.decode(R, output="codeword", errors=True)
+    assert np.array_equal(np.asarray(dec), C) and (nerr == 18).all()
+    assert np.array_equal(np.asarray(bch.decode(R)), np.asarray(M))

@@ -211,3 +211,41 @@ def test_live_rs(live_rs):
             dec, nerr = rs.decode(R, E if E.any() else None)
             assert np.array_equal(nerr, data[f"{name}/{pat}/n_errors"]), (name, pat)
             assert np.array_equal(dec, data[f"{name}/{pat}/decoded"]), (name, pat)
+
+
+def test_ref_vectors_bch_encode(ref_bch):
+    """Sage vectors for binary BCH(15, k) codes, /root/reference/tests/codes/data/bch/n15_*_sys.pkl (q = 2)."""
+    F = oracle.Field.binary(4, 0b10011, alpha=2)
+    assert len(ref_bch["names"]) >= 10
+    for name in ref_bch["names"]:
+        q, n, k, d, alpha, c = (int(v) for v in ref_bch[f"{name}/params"])
+        bch = oracle.BCH(F, n, d, c=c, alpha=alpha)
+        assert bch.k == k, name
+        assert np.array_equal(bch.P, ref_bch[f"{name}/G"][:, k:]), name
+        assert np.array_equal(bch.encode(ref_bch[f"{name}/messages"]), ref_bch[f"{name}/codewords"]), name
+        if f"{name}/short_messages" in ref_bch.files:
+            assert np.array_equal(bch.encode(ref_bch[f"{name}/short_messages"]), ref_bch[f"{name}/short_codewords"]), name
+
+
+def test_live_bch(live_bch):
+    data, meta = live_bch
+    for name, m in meta.items():
+        F = oracle.Field.binary(m["m"], m["irreducible_poly"], alpha=m["primitive_element"])
+        bch = oracle.BCH(F, m["n"], m["d"], c=m["c"], alpha=m["alpha"])
+        assert bch.k == m["k"], name
+        assert np.array_equal(bch.generator_poly, data[f"{name}/generator_poly"]), name
+        assert np.array_equal(bch.roots, data[f"{name}/roots"]), name
+        assert np.array_equal(bch.P, data[f"{name}/G"][:, m["k"]:]), name
+        assert np.array_equal(bch.encode(data[f"{name}/messages"]), data[f"{name}/codewords"]), name
+        assert np.array_equal(bch.encode(data[f"{name}/short/messages"]), data[f"{name}/short/codewords"]), name
+        pats = sorted({k[len(name) + 1:].rsplit("/", 1)[0] for k in data.files if k.startswith(name + "/") and k.endswith("/received")})
+        assert len(pats) >= 8
+        for pat in pats:
+            R, E = data[f"{name}/{pat}/received"], data[f"{name}/{pat}/erasures"]
+            raised = data[f"{name}/{pat}/raised"]
+            dec, nerr = bch.decode(R, E if E.any() else None)
+            ok = ~raised
+            assert np.array_equal(nerr[ok], data[f"{name}/{pat}/n_errors"][ok]), (name, pat)
+            assert np.array_equal(dec[ok], data[f"{name}/{pat}/decoded"][ok]), (name, pat)
+            # rows on which the reference raised ValueError are exactly the rows decoded to non-binary symbols
+            assert np.array_equal((dec >= 2).any(axis=1), raised), (name, pat)
