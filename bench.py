@@ -654,7 +654,51 @@ class Intt(Ntt):
         self.hz = self.gb.intt(self.hx)
 
 
-WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode, "intt": Intt})
+class BchDecode(RsDecode):
+    """Binary BCH(255,131), t = 18: decode 1e6 codewords with 18 bit errors each."""
+
+    metric, n_err, n_era, bytes_per_unit = "bch255_131_decode_cw_per_sec", 18, 0, 518
+
+    def __init__(self, rank, world, total=10**6):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200._dist import shard_bounds
+
+        self.gb, self.torch = gb, torch
+        self.rs = gb.BCH(255, 131)
+        lo, hi = shard_bounds(total, rank, world)
+        self.N = hi - lo
+        self.name = f"BCH(255,131) decode, {total} codewords x 18 bit errors sharded over {world} GPU(s)"
+        M = self.rs.field.Random((self.N, 131), seed=6 + rank)
+        C = self.rs.encode_device(M.to_device()).tensor.view(self.N, 255)
+        g = torch.Generator(device="cuda").manual_seed(7 + rank)
+        pos = torch.rand((self.N, 255), device="cuda", generator=g).topk(18, dim=1).indices
+        R = C.clone()
+        R.scatter_(1, pos, R.gather(1, pos) ^ 1)
+        self.E, self.C = None, C
+        self.R = gb.DeviceArray(self.rs.field, R.reshape(-1), (self.N, 255), np.uint8)
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = self.N, 1, 0, 0
+
+    def cpu_step(self, threads):
+        import oracle
+
+        n = 250 * threads
+        if not hasattr(self, "ob"):
+            self.ob = oracle.BCH(oracle.Field.binary(8, 0x11D, alpha=2), 255, 37)
+            if not hasattr(self, "cR"):
+                rng = np.random.default_rng(7)
+                C = self.ob.encode(rng.integers(0, 2, (n, 131)), threads=threads)
+                for i in range(n):
+                    C[i, rng.choice(255, 18, replace=False)] ^= 1
+                self.cR = C
+        self.ob.decode(self.cR, threads=threads)
+        return len(self.cR)
+
+    cpu_sample = "250 codewords per thread with 18 bit errors each (bch_decode_jit restatement, field GF(2), extension GF(2^8))"
+
+
+WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode, "intt": Intt, "bch_decode": BchDecode})
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -696,7 +740,9 @@ def run_reference(args):
 
         work.GF = gb.GF(P_NTT)  # host-side constants only (omega)
     threads = cpu_threads()
-    if cls in (RsDecode, RsDecodeErasures):
+    if cls is BchDecode:
+        pass  # builds its own received words in cpu_step
+    elif cls in (RsDecode, RsDecodeErasures):
         # the CPU leg needs received words: build them with the oracle itself
         import oracle
 

@@ -13,8 +13,9 @@ kernels (galois_b200/csrc).  There is no CPU fallback.
 
 from ._field import GF, DeviceArray, Field, FieldArray
 from ._lib import BackendUnavailable
+from ._linalg import poly_evaluate
 from ._ntt import intt, ntt, ntt_device
 from ._rs import BCH, ReedSolomon
 
-__all__ = ["GF", "Field", "FieldArray", "DeviceArray", "ntt", "intt", "ntt_device", "ReedSolomon", "BCH", "BackendUnavailable"]
+__all__ = ["GF", "Field", "FieldArray", "DeviceArray", "ntt", "intt", "ntt_device", "ReedSolomon", "BCH", "poly_evaluate", "BackendUnavailable"]
 __version__ = "0.1.0"

@@ -56,6 +56,8 @@ SIGNATURES = {
     "gfb_ntt_exec_host": (_int, [_vp, _int, _vp, _vp, _sz]),
     "gfb_convolve": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
     "gfb_convolve_host": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp]),
+    "gfb_poly_evaluate": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "gfb_poly_evaluate_host": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _sz]),
     "gfb_matmul": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int, _vp]),
     "gfb_matmul_host": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int]),
     "gfb_rs_create": (_int, [C.POINTER(_vp), _vp, _int, _int, _int, _u64]),

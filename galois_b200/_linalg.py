@@ -80,3 +80,30 @@ def matmul(field, A, B):
     if C.ndim == 0:
         return field(int(C.item()), dtype=dtype)
     return C
+
+
+def poly_evaluate(coeffs, x):
+    """
+    Evaluate the polynomial with degree-descending coefficients ``coeffs`` at every element of ``x`` (Horner).
+    Mirrors ``evaluate_elementwise_jit.__call__`` (/root/reference/src/galois/_polys/_dense.py:409-424), the kernel
+    behind ``Poly.__call__``: result has ``x``'s shape and dtype.
+    """
+    from ._field import FieldArray
+
+    if not isinstance(coeffs, FieldArray) or not isinstance(x, FieldArray) or type(coeffs) is not type(x):
+        raise TypeError("Arguments 'coeffs' and 'x' must be arrays over the same field.")
+    field = type(x)
+    if coeffs.ndim != 1 or coeffs.size == 0:
+        raise ValueError("Argument 'coeffs' must be a non-empty 1-D array.")
+    dtype = x.dtype
+    shape = x.shape
+    xv = field._to_dev_layout(field._prep(np.atleast_1d(x).reshape(-1).view(field), dtype))
+    cv = field._to_dev_layout(field._prep(coeffs, dtype))
+    n = int(np.prod(shape)) if shape else 1
+    out = field._alloc_out(n, dtype)
+    if n:
+        st = _lib.lib().gfb_poly_evaluate_host(field._handle(), field._elem_bytes(dtype), cv.ctypes.data, coeffs.size,
+                                               xv.ctypes.data, out.ctypes.data, n)
+        _lib.check(st, "gfb_poly_evaluate_host")
+    res = field._from_dev_layout(out, shape, dtype)
+    return res if res.ndim else field(int(res.item()), dtype=dtype)

@@ -119,6 +119,41 @@ __global__ void __launch_bounds__(kTile* kTile) k_matmul(F f, const T* __restric
     if (row < M && col < N) Cb[row * N + col] = to_store<T, E>(acc.done(f));
 }
 
+// ----------------------------------------------------------------------------------------
+// polynomial evaluation at many points (Horner): y[i] = coeffs[0] x^(nc-1) + ... + coeffs[nc-1]
+// evaluate_elementwise_jit.implementation, /root/reference/src/galois/_polys/_dense.py:432-440.
+// One thread per point; the coefficients stream through shared memory in chunks shared by the block.
+// ----------------------------------------------------------------------------------------
+constexpr int kEvalThreads = 256;
+constexpr int kEvalChunk = 512;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kEvalThreads) k_poly_eval(F f, const T* __restrict__ coeffs, size_t nc,
+                                                             const T* __restrict__ x, T* __restrict__ y, size_t n,
+                                                             size_t smem_field_bytes) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    E* sc = reinterpret_cast<E*>(reinterpret_cast<char*>(smem_raw) + smem_field_bytes);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // every thread of the block walks the same number of rounds so that the barriers line up
+    const size_t rounds = (n + stride - 1) / stride;
+    for (size_t r = 0; r < rounds; ++r) {
+        const size_t i = r * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = i < n;
+        const E xi = live ? to_elem<E, T>(x[i]) : f.zero();
+        E acc = f.zero();
+        for (size_t c0 = 0; c0 < nc; c0 += kEvalChunk) {
+            const size_t cnt = nc - c0 < (size_t)kEvalChunk ? nc - c0 : (size_t)kEvalChunk;
+            __syncthreads();
+            for (size_t j = threadIdx.x; j < cnt; j += blockDim.x) sc[j] = to_elem<E, T>(coeffs[c0 + j]);
+            __syncthreads();
+            for (size_t j = 0; j < cnt; ++j) acc = f.add(sc[j], f.mul(acc, xi));
+        }
+        if (live) y[i] = to_store<T, E>(acc);
+    }
+}
+
 template <typename F>
 static size_t smem_for(const F& f) {
     if constexpr (F::kNeedsSmem)
@@ -147,6 +182,32 @@ static gfb_status launch_matmul(F f, const void* A, const void* B, void* C, size
     k_matmul<T, F><<<grid, kTile * kTile, smem, st>>>(f, (const T*)A, (const T*)B, (T*)C, M, K, N, b_batched, fs);
     GFB_CUDA_TRY(cudaGetLastError());
     return GFB_OK;
+}
+
+template <typename T, typename F>
+static gfb_status launch_poly_eval(F f, const void* coeffs, size_t nc, const void* x, void* y, size_t n,
+                                   cudaStream_t st) {
+    using E = typename F::elem;
+    const size_t fs = smem_for(f);
+    const size_t smem = fs + kEvalChunk * sizeof(E);
+    size_t blocks = (n + kEvalThreads - 1) / kEvalThreads;
+    const size_t cap = (size_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_poly_eval<T, F><<<(unsigned)blocks, kEvalThreads, smem, st>>>(f, (const T*)coeffs, nc, (const T*)x, (T*)y, n, fs);
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+template <typename F>
+static gfb_status eval_by_width(F f, int eb, const void* coeffs, size_t nc, const void* x, void* y, size_t n,
+                                cudaStream_t st) {
+    switch (eb) {
+        case 1: return launch_poly_eval<uint8_t, F>(f, coeffs, nc, x, y, n, st);
+        case 2: return launch_poly_eval<uint16_t, F>(f, coeffs, nc, x, y, n, st);
+        case 4: return launch_poly_eval<uint32_t, F>(f, coeffs, nc, x, y, n, st);
+        case 8: return launch_poly_eval<unsigned long long, F>(f, coeffs, nc, x, y, n, st);
+    }
+    return GFB_ERR_BAD_ARG;
 }
 
 template <typename F>
@@ -216,6 +277,50 @@ gfb_status gfb_matmul(gfb_field* f, int eb, const void* A, const void* B, void* 
         case IMPL_BIN_128: return launch_matmul<u128, Binary128>(f->bin_128(), A, B, C, batch, M, K, N, b_batched, st);
     }
     return GFB_ERR_BAD_ARG;
+}
+
+gfb_status gfb_poly_evaluate(gfb_field* f, int eb, const void* coeffs, size_t nc, const void* x, void* y, size_t n,
+                             void* stream) {
+    using namespace gfb;
+    if (!f || !coeffs || nc == 0) return GFB_ERR_BAD_ARG;
+    if (n == 0) return GFB_OK;
+    if (!x || !y) return GFB_ERR_BAD_ARG;
+    if (!width_ok(f, eb)) return GFB_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (f->impl) {
+        case IMPL_PRIME_M31: return eval_by_width(f->prime_m31(), eb, coeffs, nc, x, y, n, st);
+        case IMPL_PRIME_BARRETT: return eval_by_width(f->prime_barrett(), eb, coeffs, nc, x, y, n, st);
+        case IMPL_BIN_LUT: return eval_by_width(f->bin_lut(), eb, coeffs, nc, x, y, n, st);
+        case IMPL_BIN_CALC: return eval_by_width(f->bin_calc(), eb, coeffs, nc, x, y, n, st);
+        case IMPL_BIN_128: return launch_poly_eval<u128, Binary128>(f->bin_128(), coeffs, nc, x, y, n, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
+gfb_status gfb_poly_evaluate_host(gfb_field* f, int eb, const void* coeffs, size_t nc, const void* x, void* y,
+                                  size_t n) {
+    if (!f || !coeffs || nc == 0) return GFB_ERR_BAD_ARG;
+    if (n == 0) return GFB_OK;
+    if (!x || !y) return GFB_ERR_BAD_ARG;
+    char *dc = nullptr, *dx = nullptr, *dy = nullptr;
+    GFB_CUDA_TRY(cudaMalloc((void**)&dc, nc * (size_t)eb + 16));
+    cudaError_t e = cudaMalloc((void**)&dx, n * (size_t)eb + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dy, n * (size_t)eb + 16);
+    gfb_status st = GFB_OK;
+    if (e == cudaSuccess) e = cudaMemcpy(dc, coeffs, nc * (size_t)eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * (size_t)eb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        st = gfb_poly_evaluate(f, eb, dc, nc, dx, dy, n, nullptr);
+        if (st == GFB_OK) e = cudaMemcpy(y, dy, n * (size_t)eb, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dc);
+    cudaFree(dx);
+    cudaFree(dy);
+    if (e != cudaSuccess) {
+        gfb::set_last_error("gfb_poly_evaluate_host", e);
+        return GFB_ERR_CUDA;
+    }
+    return st;
 }
 
 // host variants: one-shot copies (these operands are small next to the element-wise arrays)

@@ -157,6 +157,13 @@ gfb_status gfb_convolve(gfb_field* f, int elem_bytes, const void* a, size_t na, 
                         size_t nb, void* out, void* stream);
 gfb_status gfb_convolve_host(gfb_field* f, int elem_bytes, const void* a, size_t na, const void* b,
                              size_t nb, void* out);
+/* y[i] = coeffs[0] x[i]^(nc-1) + ... + coeffs[nc-1]: one polynomial (degree-descending coefficients) evaluated at n
+ * points by Horner's rule.  evaluate_elementwise_jit (_polys/_dense.py:404-440) behind Poly.__call__
+ * (SURVEY.md §8f rank 2). */
+gfb_status gfb_poly_evaluate(gfb_field* f, int elem_bytes, const void* coeffs, size_t nc, const void* x,
+                             void* y, size_t n, void* stream);
+gfb_status gfb_poly_evaluate_host(gfb_field* f, int elem_bytes, const void* coeffs, size_t nc, const void* x,
+                                  void* y, size_t n);
 /* C[batch][M][N] = A[batch][M][K] · B[batch or 1][K][N] over the field.  matmul_jit
  * (_domains/_linalg.py:180-308).  b_batched = 0 broadcasts one B to every batch. */
 gfb_status gfb_matmul(gfb_field* f, int elem_bytes, const void* A, const void* B, void* C,

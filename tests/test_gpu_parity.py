@@ -493,3 +493,30 @@ def test_bch_255_131_bulk_vs_oracle():
     dec, nerr = bch.decode(R, output="codeword", errors=True)
     assert np.array_equal(np.asarray(dec), C) and (nerr == 18).all()
     assert np.array_equal(np.asarray(bch.decode(R)), np.asarray(M))
+
+
+def test_poly_evaluate(live_linalg):
+    """Horner evaluation (evaluate_elementwise_jit behind Poly.__call__) vs the live
+    reference's Poly(...)(x) and vs the oracle on larger cases over several fields."""
+    d = live_linalg
+    GF = gb.GF(2**8)
+    n_cases = len({k.split("/")[1] for k in d.files if k.startswith("eval/")})
+    assert n_cases >= 10
+    for i in range(n_cases):
+        y = gb.poly_evaluate(GF(d[f"eval/{i}/coeffs"]), GF(d[f"eval/{i}/x"]))
+        assert type(y) is GF and np.array_equal(np.asarray(y), d[f"eval/{i}/y"]), i
+    for name in ("GF(2147483647)", "GF(998244353)", "GF(2^8)", "GF(2^32)", "GF(7)"):
+        G = make_gf(name)
+        F = oracle_field(name)
+        for nc, n in [(1, 5), (2, 1000), (33, 4097), (1500, 20000)]:
+            c = G.Random(nc, seed=nc)
+            x = G.Random(n, seed=n + 1)
+            y = gb.poly_evaluate(c, x)
+            assert type(y) is G and y.dtype == x.dtype and y.shape == x.shape
+            assert np.array_equal(np.asarray(y).astype(np.int64), F.poly_evaluate(np.asarray(c), np.asarray(x))), (name, nc, n)
+    # multipoint evaluation at the N-th roots of unity is the NTT (tests/fields/test_fft.py:33-45)
+    G = gb.GF(998244353)
+    x = G.Random(256, seed=5)
+    w = int(G.primitive_root_of_unity(256))
+    pts = G([pow(w, k, G.order) for k in range(256)])
+    assert np.array_equal(np.asarray(gb.poly_evaluate(G(np.asarray(x)[::-1].copy()), pts)), np.asarray(gb.ntt(x)))
