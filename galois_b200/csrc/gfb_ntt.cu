@@ -32,13 +32,14 @@ struct gfb_ntt_plan {
     int log_n;
     uint32_t p;
     uint32_t omega, scale;
-    bool fast;             // four-step 1024 x 1024 path available
+    bool fast;             // four-step n1 x 1024 path available (2^15 <= N <= 2^20, p < 2^31)
     bool lazy;             // p < 2^30
     // generic path
     uint32_t* d_pow;       // omega^e, e < max(n/2, 1)
     // fast path
-    uint2* d_tw4;          // [k*1024 + c] = (scale * omega^(c k), shoup)
-    uint2* d_zt;           // [k1*32 + t] = (zeta^(t k1), shoup), zeta = omega^1024
+    uint2* d_tw4;          // [k*1024 + c] = (scale * omega^(c k), shoup), k < n1 = N/1024
+    uint2* d_zt;           // pass 2: [k1*32 + t] = (zeta2^(t k1), shoup), zeta2 = omega^n1 (1024th root), k1 < 32
+    uint2* d_zt1;          // pass 1: [k1*32 + t] = (zeta1^(t k1), shoup), zeta1 = omega^1024 (n1-th root), k1 < n1/32
     uint32_t rho[16], rho_sh[16];  // rho^e, rho = zeta^32 (primitive 32nd root), with Shoup companions
 };
 
@@ -59,19 +60,19 @@ __global__ void k_build_pow(PrimeBarrett f, uint32_t omega, uint32_t* out, size_
     if (i < count) out[i] = f.pow_u64(omega, i);
 }
 
-// tw4[k*1024 + c] = scale * omega^(c*k)
-__global__ void k_build_tw4(PrimeBarrett f, uint32_t omega, uint32_t scale, uint2* out) {
+// tw4[k*1024 + c] = scale * omega^(c*k), k < n1
+__global__ void k_build_tw4(PrimeBarrett f, uint32_t omega, uint32_t scale, uint2* out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ((size_t)1 << 20)) return;
+    if (i >= n) return;
     unsigned long long k = i >> 10, c = i & 1023;
     uint32_t w = f.mul(f.pow_u64(omega, k * c), scale);
     out[i] = make_uint2(w, shoup(w, f.p));
 }
 
-// zt[k1*32 + t] = zeta^(t*k1)
-__global__ void k_build_zt(PrimeBarrett f, uint32_t zeta, uint2* out) {
+// zt[k1*32 + t] = zeta^(t*k1), k1 < count/32
+__global__ void k_build_zt(PrimeBarrett f, uint32_t zeta, uint2* out, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 1024) return;
+    if (i >= count) return;
     unsigned long long k1 = i >> 5, t = i & 31;
     uint32_t w = f.pow_u64(zeta, k1 * t);
     out[i] = make_uint2(w, shoup(w, f.p));
@@ -169,19 +170,25 @@ struct Mod {
     }
 };
 
-__host__ __device__ constexpr int brev5(int i) {
-    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+// In-register R-point DIT NTT, R = 2^LOG_R <= 32.  On entry v[brev(i)] = x[i]; on exit v[k] = sum_i x[i] rho_R^(i k)
+// with rho_R = rho^(32/R): the twiddle of butterfly j in stage S is rho_R^(j R / 2^(S+1)) = rho^(j * (16 >> S)) for
+// every R, so all sizes share the 16 radix-32 constants.
+template <int LOG_R>
+__host__ __device__ constexpr int brev(int i) {
+    int r = 0;
+    for (int b = 0; b < LOG_R; ++b) r |= ((i >> b) & 1) << (LOG_R - 1 - b);
+    return r;
 }
+__host__ __device__ constexpr int brev5(int i) { return brev<5>(i); }
 
-// In-register 32-point DIT NTT.  On entry v[brev5(i)] = x[i]; on exit v[k] = sum_i x[i] rho^(i k).
-template <bool LAZY, int S>
-__device__ __forceinline__ void radix32_stage(uint32_t (&v)[32], const Mod<LAZY>& md, const Radix32Roots& rt) {
+template <bool LAZY, int LOG_R, int S>
+__device__ __forceinline__ void radix_stage(uint32_t (&v)[1 << LOG_R], const Mod<LAZY>& md, const Radix32Roots& rt) {
     constexpr int half = 1 << S;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {  // the 16 butterflies of stage S, flat so that every index is static
+    for (int g = 0; g < (1 << LOG_R) / 2; ++g) {  // flat loop over the butterflies of stage S: every index is static
         const int j = g & (half - 1);
         const int k = (g >> S) << (S + 1);
-        const int e = j * (16 >> S);  // twiddle rho^(j * 32 / (2*half))
+        const int e = j * (16 >> S);
         if (e == 0)
             md.bfly1(v[k + j], v[k + j + half]);
         else
@@ -189,84 +196,87 @@ __device__ __forceinline__ void radix32_stage(uint32_t (&v)[32], const Mod<LAZY>
     }
 }
 
-template <bool LAZY>
-__device__ __forceinline__ void radix32(uint32_t (&v)[32], const Mod<LAZY>& md, const Radix32Roots& rt) {
-    radix32_stage<LAZY, 0>(v, md, rt);
-    radix32_stage<LAZY, 1>(v, md, rt);
-    radix32_stage<LAZY, 2>(v, md, rt);
-    radix32_stage<LAZY, 3>(v, md, rt);
-    radix32_stage<LAZY, 4>(v, md, rt);
+template <bool LAZY, int LOG_R>
+__device__ __forceinline__ void radixR(uint32_t (&v)[1 << LOG_R], const Mod<LAZY>& md, const Radix32Roots& rt) {
+    if constexpr (LOG_R > 0) radix_stage<LAZY, LOG_R, 0>(v, md, rt);
+    if constexpr (LOG_R > 1) radix_stage<LAZY, LOG_R, 1>(v, md, rt);
+    if constexpr (LOG_R > 2) radix_stage<LAZY, LOG_R, 2>(v, md, rt);
+    if constexpr (LOG_R > 3) radix_stage<LAZY, LOG_R, 3>(v, md, rt);
+    if constexpr (LOG_R > 4) radix_stage<LAZY, LOG_R, 4>(v, md, rt);
 }
 
-constexpr int kRowStride = 1058;  // uint32 words per shared-memory row (1024 + 32 pad + 2: see file header)
+constexpr int kRowStride = 1058;  // uint32 words per shared-memory row (1024 + 32 pad + 2)
 __device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
 
-// ---- 1024-point NTT of 16 vectors held in one shared-memory tile -------------------------------
-// Thread mapping: w = tid & 15 selects the vector (a tile row), tq = tid >> 4 (0..15) and the
-// sub-transform index s in {0,1} select t = tq + 16 s; the two half-warps therefore work on adjacent t.
-// Vector w lives at tile[w*kRowStride + padi(j)], j in [0,1024): with kRowStride = 2 (mod 32) and one
-// pad word per 32 elements, every access below is bank-conflict free:
+// ---- n-point NTT (n = RA x 32, RA = 2^LOG_RA <= 32) of 16 vectors held in one shared-memory tile ------------------
+// Thread mapping: w = tid & 15 selects the vector (a tile row), tq = tid >> 4 (0..15) and the sub-transform index
+// s in {0,1} select t = tq + 16 s; the two half-warps therefore work on adjacent t.  Vector w lives at
+// tile[w*kRowStride + padi(j)]: with kRowStride = 2 (mod 32) and one pad word per 32 elements, every access is
+// bank-conflict free:
 //   round A  (j = t + 32 a, lanes (w, t|t+1))  -> bank 2w + t + a     (even / odd halves)
-//   round B  (j = b + 32 t, lanes (w, t|t+1))  -> bank 2w + b + t
+//   round B  (j = b + 32 k1, lanes (w, k1|k1+1)) -> bank 2w + b + k1
 //   row-wise (j = 32 consecutive, fixed w)     -> 32 consecutive words
-// n = 1024 = 32 x 32:  X[k1 + 32 k0] = sum_{i0} rho^(i0 k0) zeta^(i0 k1) sum_{i1} x[32 i1 + i0] rho^(i1 k1).
+// X[k1 + RA k0] = sum_{i0<32} rho^(i0 k0) zeta^(i0 k1) sum_{i1<RA} x[32 i1 + i0] rho_RA^(i1 k1),  zeta = omega_n.
 
 constexpr int kFastThreads = 256;
 constexpr int kTileW = 16;
 constexpr size_t kFastSmem = (size_t)kTileW * kRowStride * sizeof(uint32_t);
 
 // second half of round A: twiddle by zeta^(t k1) and park Y[k1] at j = t + 32 k1
-template <bool LAZY>
-__device__ __forceinline__ void round_a_store(uint32_t* row, int t, const uint32_t (&v)[32], const Mod<LAZY>& md,
-                                              const uint2* __restrict__ zt) {
+template <bool LAZY, int LOG_RA>
+__device__ __forceinline__ void round_a_store(uint32_t* row, int t, const uint32_t (&v)[1 << LOG_RA],
+                                              const Mod<LAZY>& md, const uint2* __restrict__ zt) {
     row[t] = v[0];
 #pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
+    for (int k1 = 1; k1 < (1 << LOG_RA); ++k1) {
         const uint2 z = __ldg(&zt[k1 * 32 + t]);
         row[t + 33 * k1] = md.mul(v[k1], z.x, z.y);
     }
 }
 
-// pass 1: column NTTs + four-step twiddle.  One CTA per (transform, 16-column tile).  Lanes run along the 16
-// columns, so the strided global reads (64 B segments) go straight into registers and the results go straight
-// from registers to the workspace: the tile is only used for the exchange between the two radix-32 rounds.
-template <typename T, bool LAZY, int OCC>
-__global__ void __launch_bounds__(kFastThreads, OCC)
+// pass 1: column NTTs of length n1 = 32 RA + four-step twiddle.  One CTA per (transform, 16-column tile); N = n1 x 1024.
+// Lanes run along the 16 columns, so the strided global reads (64 B segments) go straight into registers and the
+// results go straight from registers to the workspace: the tile is only used for the exchange between the rounds.
+template <typename T, bool LAZY, int LOG_RA>
+__global__ void __launch_bounds__(kFastThreads, 2)
     k_ntt_pass1(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint2* __restrict__ tw4,
                 const T* __restrict__ x, uint32_t* __restrict__ ws) {
+    constexpr int RA = 1 << LOG_RA;
+    constexpr int LOG_N = LOG_RA + 15;
     extern __shared__ uint32_t tile[];
     const size_t transform = blockIdx.x >> 6;
     const int c0 = (blockIdx.x & 63) * kTileW;
     const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
-    const T* src = x + (transform << 20) + c0 + w;
-    uint32_t* dst = ws + (transform << 20) + c0 + w;
+    const T* src = x + (transform << LOG_N) + c0 + w;
+    uint32_t* dst = ws + (transform << LOG_N) + c0 + w;
     const uint2* twc = tw4 + c0 + w;
     uint32_t* row = tile + w * kRowStride;
-    uint32_t v[32];
     {
-        // x[(32 a + t) * 1024 + c]: element i1 = a of the sub-transform i0 = t.  Both sub-transforms' loads
-        // (64 independent 4-byte loads per thread) are issued before any arithmetic: one DRAM latency per CTA.
-        uint32_t u[32];
+        // x[(32 a + t) * 1024 + c]: element i1 = a of the sub-transform i0 = t.  Both sub-transforms' loads are
+        // issued before any arithmetic (up to 64 independent 4-byte loads per thread): one DRAM latency per CTA.
+        uint32_t v[RA], u[RA];
 #pragma unroll
-        for (int a = 0; a < 32; ++a) v[brev5(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq) * 1024);
+        for (int a = 0; a < RA; ++a) v[brev<LOG_RA>(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq) * 1024);
 #pragma unroll
-        for (int a = 0; a < 32; ++a) u[brev5(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq + 16) * 1024);
-        radix32<LAZY>(v, md, rt);
-        round_a_store<LAZY>(row, tq, v, md, zt);
-        radix32<LAZY>(u, md, rt);
-        round_a_store<LAZY>(row, tq + 16, u, md, zt);
+        for (int a = 0; a < RA; ++a) u[brev<LOG_RA>(a)] = (uint32_t)__ldcs(src + (size_t)(32 * a + tq + 16) * 1024);
+        radixR<LAZY, LOG_RA>(v, md, rt);
+        round_a_store<LAZY, LOG_RA>(row, tq, v, md, zt);
+        radixR<LAZY, LOG_RA>(u, md, rt);
+        round_a_store<LAZY, LOG_RA>(row, tq + 16, u, md, zt);
     }
     __syncthreads();
+    uint32_t v[32];
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
-        const int t = tq + 16 * s;  // k1
+        const int k1 = tq + 16 * s;
+        if (k1 >= RA) break;  // n1 < 1024: fewer than 32 second-round transforms per vector
 #pragma unroll
-        for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
-        radix32<LAZY>(v, md, rt);
-        // k = k1 + 32 k0; multiply by scale * omega^(c k) and store ws[k][c]
+        for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * k1 + b];
+        radixR<LAZY, 5>(v, md, rt);
+        // k = k1 + RA k0; multiply by scale * omega^(c k) and store ws[k][c]
 #pragma unroll
         for (int k0 = 0; k0 < 32; ++k0) {
-            const size_t k = (size_t)(t + 32 * k0);
+            const size_t k = (size_t)(k1 + RA * k0);
             const uint2 tw = __ldg(twc + k * 1024);
             uint32_t val = md.mul(v[k0], tw.x, tw.y);
             if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
@@ -275,19 +285,21 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
     }
 }
 
-// pass 2: row NTTs + transposed store.  One CTA per (transform, 16-row tile).  The 16 rows are contiguous in
-// the workspace, so they are staged through the tile (coalesced along the row, transposed by the tile layout);
-// the outputs X[k1 + 1024 k2] have the 16 rows (k1) innermost and go straight from registers to global memory.
-template <typename T, bool LAZY, int OCC>
-__global__ void __launch_bounds__(kFastThreads, OCC)
+// pass 2: the n1 row NTTs of length 1024 + transposed store.  One CTA per (transform, 16-row tile).  The 16 rows are
+// contiguous in the workspace, so they are staged through the tile (coalesced along the row, transposed by the tile
+// layout); the outputs X[k1 + n1 k2] have the 16 rows (k1) innermost and go straight from registers to global memory.
+template <typename T, bool LAZY>
+__global__ void __launch_bounds__(kFastThreads, 2)
     k_ntt_pass2(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint32_t* __restrict__ ws,
-                T* __restrict__ y) {
+                T* __restrict__ y, int log_n1) {
     extern __shared__ uint32_t tile[];
-    const size_t transform = blockIdx.x >> 6;
-    const int k1_0 = (blockIdx.x & 63) * kTileW;
-    const uint32_t* src = ws + (transform << 20) + (size_t)k1_0 * 1024;
+    const int tiles_log = log_n1 - 4;  // 16-row tiles per transform
+    const size_t transform = blockIdx.x >> tiles_log;
+    const int k1_0 = (int)(blockIdx.x & ((1u << tiles_log) - 1u)) * kTileW;
+    const size_t n1 = (size_t)1 << log_n1;
+    const uint32_t* src = ws + (transform << (log_n1 + 10)) + (size_t)k1_0 * 1024;
     const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
-    T* dst = y + (transform << 20) + k1_0 + w;
+    T* dst = y + (transform << (log_n1 + 10)) + k1_0 + w;
     // 16 rows x 1024 contiguous words = 4096 uint4: 16 per thread, consecutive threads consecutive uint4
     {
         const uint4* src4 = reinterpret_cast<const uint4*>(src);
@@ -311,8 +323,8 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
         const int t = tq + 16 * s;
 #pragma unroll
         for (int a = 0; a < 32; ++a) v[brev5(a)] = row[t + 33 * a];
-        radix32<LAZY>(v, md, rt);
-        round_a_store<LAZY>(row, t, v, md, zt);  // in place: thread (w, t) owns positions {t + 32 a}
+        radixR<LAZY, 5>(v, md, rt);
+        round_a_store<LAZY, 5>(row, t, v, md, zt);  // in place: thread (w, t) owns positions {t + 32 a}
     }
     __syncthreads();
 #pragma unroll 1
@@ -320,43 +332,40 @@ __global__ void __launch_bounds__(kFastThreads, OCC)
         const int t = tq + 16 * s;  // k1 of the inner transform
 #pragma unroll
         for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
-        radix32<LAZY>(v, md, rt);
+        radixR<LAZY, 5>(v, md, rt);
 #pragma unroll
-        for (int k0 = 0; k0 < 32; ++k0) dst[(size_t)(t + 32 * k0) * 1024] = (T)md.canon(v[k0]);
+        for (int k0 = 0; k0 < 32; ++k0) dst[(size_t)(t + 32 * k0) * n1] = (T)md.canon(v[k0]);
     }
 }
 
-// Resident CTAs per SM for the fast-path kernels: 3 caps registers at 80 (a few spills), 2 leaves 128.
-// GFB_NTT_OCC=2|3 overrides the default for tuning runs.
-static int ntt_occupancy() {
-    static int occ = 0;
-    if (occ == 0) {
-        const char* e = getenv("GFB_NTT_OCC");
-        occ = (e && e[0] == '3') ? 3 : 2;
-    }
-    return occ;
-}
+// transforms per pass-1 / pass-2 launch pair: 74 * 2^20 elements of uint32 workspace; at N = 2^20 that is
+// 74 * 64 CTAs = 16 full waves of 2 CTAs/SM x 148 SMs
+static size_t fast_chunk(const gfb_ntt_plan* pl) { return (size_t)kNttChunk << (20 - pl->log_n); }
 
-template <typename T, bool LAZY, int OCC>
-static gfb_status run_fast_occ(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+template <typename T, bool LAZY, int LOG_RA>
+static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
     Mod<LAZY> md{pl->p, pl->p * 2u};
     Radix32Roots rt;
     memcpy(rt.w, pl->rho, sizeof(rt.w));
     memcpy(rt.ws, pl->rho_sh, sizeof(rt.ws));
     static bool attr_set = false;
     if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kFastSmem));
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kFastSmem));
         attr_set = true;
     }
-    for (size_t off = 0; off < batch; off += kNttChunk) {
-        const size_t cnt = batch - off < (size_t)kNttChunk ? batch - off : (size_t)kNttChunk;
-        const unsigned grid = (unsigned)(cnt * 64);
-        k_ntt_pass1<T, LAZY, OCC>
-            <<<grid, kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, pl->d_tw4, x + (off << 20), ws);
-        k_ntt_pass2<T, LAZY, OCC><<<grid, kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, ws, y + (off << 20));
+    const int log_n1 = LOG_RA + 5;
+    const size_t chunk = fast_chunk(pl);
+    for (size_t off = 0; off < batch; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        const T* xin = x + (off << pl->log_n);
+        T* yout = y + (off << pl->log_n);
+        k_ntt_pass1<T, LAZY, LOG_RA>
+            <<<(unsigned)(cnt * 64), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt1, pl->d_tw4, xin, ws);
+        k_ntt_pass2<T, LAZY><<<(unsigned)(cnt << (log_n1 - 4)), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, ws, yout,
+                                                                                             log_n1);
     }
     GFB_CUDA_TRY(cudaGetLastError());
     return GFB_OK;
@@ -364,8 +373,15 @@ static gfb_status run_fast_occ(gfb_ntt_plan* pl, const T* x, T* y, size_t batch,
 
 template <typename T, bool LAZY>
 static gfb_status run_fast_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
-    return ntt_occupancy() == 2 ? run_fast_occ<T, LAZY, 2>(pl, x, y, batch, ws, st)
-                                : run_fast_occ<T, LAZY, 3>(pl, x, y, batch, ws, st);
+    switch (pl->log_n - 15) {
+        case 0: return run_fast_ra<T, LAZY, 0>(pl, x, y, batch, ws, st);
+        case 1: return run_fast_ra<T, LAZY, 1>(pl, x, y, batch, ws, st);
+        case 2: return run_fast_ra<T, LAZY, 2>(pl, x, y, batch, ws, st);
+        case 3: return run_fast_ra<T, LAZY, 3>(pl, x, y, batch, ws, st);
+        case 4: return run_fast_ra<T, LAZY, 4>(pl, x, y, batch, ws, st);
+        case 5: return run_fast_ra<T, LAZY, 5>(pl, x, y, batch, ws, st);
+    }
+    return GFB_ERR_BAD_ARG;
 }
 
 template <typename T>
@@ -447,7 +463,7 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
     pl->p = p;
     pl->omega = (uint32_t)omega;
     pl->scale = (uint32_t)scale;
-    pl->fast = (n == ((size_t)1 << 20)) && p < (1u << 31);
+    pl->fast = pl->log_n >= 15 && pl->log_n <= 20 && p < (1u << 31);
     pl->lazy = p < (1u << 30);
     PrimeBarrett fb = f->prime_barrett();
     const size_t npow = n / 2 ? n / 2 : 1;
@@ -459,17 +475,23 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
             e = cudaGetLastError();
         }
     } else {
-        const uint32_t zeta = host_powmod(pl->omega, 1024, p);
-        const uint32_t rho = host_powmod(zeta, 32, p);
+        // N = n1 x 1024: zeta1 = omega^1024 has order n1 (column transforms), zeta2 = omega^n1 has order 1024 (row
+        // transforms), rho = omega^(N/32) is the 32nd root shared by every in-register radix stage
+        const size_t n1 = n >> 10;
+        const uint32_t zeta1 = host_powmod(pl->omega, 1024, p);
+        const uint32_t zeta2 = host_powmod(pl->omega, n1, p);
+        const uint32_t rho = host_powmod(pl->omega, n / 32, p);
         for (int i = 0; i < 16; ++i) {
             pl->rho[i] = host_powmod(rho, i, p);
             pl->rho_sh[i] = (uint32_t)((((unsigned long long)pl->rho[i]) << 32) / p);
         }
-        e = cudaMalloc((void**)&pl->d_tw4, ((size_t)1 << 20) * sizeof(uint2));
+        e = cudaMalloc((void**)&pl->d_tw4, n * sizeof(uint2));
         if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt, 1024 * sizeof(uint2));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt1, n1 * sizeof(uint2));
         if (e == cudaSuccess) {
-            k_build_tw4<<<4096, 256>>>(fb, pl->omega, pl->scale, pl->d_tw4);
-            k_build_zt<<<4, 256>>>(fb, zeta, pl->d_zt);
+            k_build_tw4<<<(unsigned)((n + 255) / 256), 256>>>(fb, pl->omega, pl->scale, pl->d_tw4, n);
+            k_build_zt<<<4, 256>>>(fb, zeta2, pl->d_zt, 1024);
+            k_build_zt<<<(unsigned)((n1 + 255) / 256), 256>>>(fb, zeta1, pl->d_zt1, (int)n1);
             e = cudaGetLastError();
         }
     }
@@ -488,6 +510,7 @@ void gfb_ntt_plan_destroy(gfb_ntt_plan* pl) {
     if (pl->d_pow) cudaFree(pl->d_pow);
     if (pl->d_tw4) cudaFree(pl->d_tw4);
     if (pl->d_zt) cudaFree(pl->d_zt);
+    if (pl->d_zt1) cudaFree(pl->d_zt1);
     free(pl);
 }
 
@@ -496,7 +519,8 @@ size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t ba
     (void)elem_bytes;
     if (!pl || batch == 0) return 0;
     if (pl->fast) {
-        const size_t rows = batch < (size_t)kNttChunk ? batch : (size_t)kNttChunk;
+        const size_t chunk = fast_chunk(pl);
+        const size_t rows = batch < chunk ? batch : chunk;
         return rows * pl->n * sizeof(uint32_t);
     }
     if (pl->n <= 2) return 0;

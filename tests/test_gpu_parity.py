@@ -520,3 +520,22 @@ def test_poly_evaluate(live_linalg):
     w = int(G.primitive_root_of_unity(256))
     pts = G([pow(w, k, G.order) for k in range(256)])
     assert np.array_equal(np.asarray(gb.poly_evaluate(G(np.asarray(x)[::-1].copy()), pts)), np.asarray(gb.ntt(x)))
+
+
+@pytest.mark.parametrize("log_n", [15, 16, 17, 18, 19, 20])
+def test_ntt_four_step_sizes(log_n):
+    """Every size of the four-step fast path (N = n1 x 1024, n1 = 32..1024) vs the oracle, batched, forward and
+    inverse, 4- and 8-byte storage, lazy (p < 2^30) and strict (2^30 <= p < 2^31) arithmetic."""
+    n = 1 << log_n
+    for p in (998244353, 2013265921):
+        GF = gb.GF(p)
+        F = oracle.Field.prime(p)
+        omega = int(GF.primitive_root_of_unity(n))
+        for dtype in (np.uint32, np.int64):
+            x = GF.Random((3, n), seed=log_n, dtype=dtype)
+            X = gb.ntt(x)
+            assert type(X) is GF and X.dtype == dtype
+            assert np.array_equal(np.asarray(X).astype(np.int64), F.fft(np.asarray(x), omega, threads=3)), (log_n, p, dtype)
+            assert np.array_equal(np.asarray(gb.intt(X)), np.asarray(x)), (log_n, p, dtype)
+        d = x.to_device()
+        assert np.array_equal(np.asarray(gb.ntt_device(gb.ntt_device(d), inverse=True).cpu()), np.asarray(x))
