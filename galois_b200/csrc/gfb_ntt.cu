@@ -288,18 +288,20 @@ __global__ void __launch_bounds__(kFastThreads, 2)
 // pass 2: the n1 row NTTs of length 1024 + transposed store.  One CTA per (transform, 16-row tile).  The 16 rows are
 // contiguous in the workspace, so they are staged through the tile (coalesced along the row, transposed by the tile
 // layout); the outputs X[k1 + n1 k2] have the 16 rows (k1) innermost and go straight from registers to global memory.
-template <typename T, bool LAZY>
+template <typename T, bool LAZY, bool SMALL>
 __global__ void __launch_bounds__(kFastThreads, 2)
     k_ntt_pass2(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint32_t* __restrict__ ws,
-                T* __restrict__ y, int log_n1) {
+                T* __restrict__ y, int log_n1, size_t rows_total) {
     extern __shared__ uint32_t tile[];
-    const int tiles_log = log_n1 - 4;  // 16-row tiles per transform
-    const size_t transform = blockIdx.x >> tiles_log;
-    const int k1_0 = (int)(blockIdx.x & ((1u << tiles_log) - 1u)) * kTileW;
+    // the workspace is [transform][k1 < n1][1024]: rows are contiguous across transforms, a tile is 16 consecutive rows
+    const size_t row0 = (size_t)blockIdx.x * kTileW;
     const size_t n1 = (size_t)1 << log_n1;
-    const uint32_t* src = ws + (transform << (log_n1 + 10)) + (size_t)k1_0 * 1024;
+    const uint32_t* src = ws + row0 * 1024;
     const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
-    T* dst = y + (transform << (log_n1 + 10)) + k1_0 + w;
+    const size_t my_row = row0 + w;
+    // output X[transform][k1 + n1 k2]; with n1 >= 16 the 16 rows of a tile are 16 consecutive k1 of one transform
+    T* dst = y + ((my_row >> log_n1) << (log_n1 + 10)) + (my_row & (n1 - 1));
+    const bool row_live = !SMALL || my_row < rows_total;
     // 16 rows x 1024 contiguous words = 4096 uint4: 16 per thread, consecutive threads consecutive uint4
     {
         const uint4* src4 = reinterpret_cast<const uint4*>(src);
@@ -307,7 +309,8 @@ __global__ void __launch_bounds__(kFastThreads, 2)
         for (int it = 0; it < 16; ++it) {
             const int e = it * kFastThreads + threadIdx.x;  // uint4 index within the tile
             const int ww = e >> 8, i = (e & 255) * 4;
-            const uint4 q = __ldg(src4 + e);
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (!SMALL || row0 + ww < rows_total) q = __ldg(src4 + e);
             uint32_t* d = tile + ww * kRowStride + padi(i);  // i % 4 == 0: the four words share one pad offset
             d[0] = q.x;
             d[1] = q.y;
@@ -333,8 +336,107 @@ __global__ void __launch_bounds__(kFastThreads, 2)
 #pragma unroll
         for (int b = 0; b < 32; ++b) v[brev5(b)] = row[33 * t + b];
         radixR<LAZY, 5>(v, md, rt);
+        if (row_live) {
 #pragma unroll
-        for (int k0 = 0; k0 < 32; ++k0) dst[(size_t)(t + 32 * k0) * n1] = (T)md.canon(v[k0]);
+            for (int k0 = 0; k0 < 32; ++k0) dst[(size_t)(t + 32 * k0) * n1] = (T)md.canon(v[k0]);
+        }
+    }
+}
+
+// pass 1 for short columns, n1 = 2^LOG_N1 in {2, 4, 8, 16} (N = 2^11 .. 2^14): one thread per column does the whole
+// n1-point transform in registers; lanes run along the row, so every access is a full 128-byte line.
+template <typename T, bool LAZY, int LOG_N1>
+__global__ void __launch_bounds__(256)
+    k_ntt_pass1_small(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ tw4, const T* __restrict__ x,
+                      uint32_t* __restrict__ ws, size_t columns_total) {
+    constexpr int N1 = 1 << LOG_N1;
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // transform * 1024 + c
+    if (col >= columns_total) return;
+    const size_t transform = col >> 10, c = col & 1023;
+    const T* src = x + (transform << (LOG_N1 + 10)) + c;
+    uint32_t* dst = ws + (transform << (LOG_N1 + 10)) + c;
+    uint32_t v[N1];
+#pragma unroll
+    for (int r = 0; r < N1; ++r) v[brev<LOG_N1>(r)] = (uint32_t)__ldcs(src + (size_t)r * 1024);
+    radixR<LAZY, LOG_N1>(v, md, rt);
+#pragma unroll
+    for (int k = 0; k < N1; ++k) {
+        const uint2 tw = __ldg(tw4 + (size_t)k * 1024 + c);
+        uint32_t val = md.mul(v[k], tw.x, tw.y);
+        if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
+        dst[(size_t)k * 1024] = val;
+    }
+}
+
+// whole transforms of N = 32 RA <= 1024 points, 16 per CTA, in one kernel: coalesced staged load, the two rounds,
+// results parked in the tile in natural order, coalesced store (with the optional 1/N scale).
+template <typename T, bool LAZY, int LOG_RA>
+__global__ void __launch_bounds__(kFastThreads, 2)
+    k_ntt_small(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const T* __restrict__ x, T* __restrict__ y,
+                size_t batch, uint32_t scale, uint32_t scale_sh) {
+    constexpr int RA = 1 << LOG_RA;
+    constexpr int LOG_N = LOG_RA + 5;
+    constexpr int N = 1 << LOG_N;
+    extern __shared__ uint32_t tile[];
+    const size_t row0 = (size_t)blockIdx.x * kTileW;
+    const size_t rows_here = batch - row0 < (size_t)kTileW ? batch - row0 : (size_t)kTileW;
+    const T* src = x + row0 * N;
+    T* dst = y + row0 * N;
+    const int w = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    for (int e = threadIdx.x; e < kTileW * N; e += kFastThreads) {
+        const int ww = e >> LOG_N, i = e & (N - 1);
+        tile[ww * kRowStride + padi(i)] = (size_t)ww < rows_here ? (uint32_t)src[e] : 0u;
+    }
+    __syncthreads();
+    uint32_t* row = tile + w * kRowStride;
+    {
+        uint32_t v[RA];
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const int t = tq + 16 * s;
+#pragma unroll
+            for (int a = 0; a < RA; ++a) v[brev<LOG_RA>(a)] = row[t + 33 * a];
+            radixR<LAZY, LOG_RA>(v, md, rt);
+            round_a_store<LAZY, LOG_RA>(row, t, v, md, zt);
+        }
+    }
+    __syncthreads();
+    // round B reads rows {33 k1 + b} and writes positions k1 + RA k0 that other threads still read: keep both
+    // sub-transforms in registers until every thread has finished reading
+    uint32_t v0[32], v1[32];
+    const bool has0 = tq < RA, has1 = tq + 16 < RA;
+    if (has0) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) v0[brev5(b)] = row[33 * tq + b];
+    }
+    if (has1) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) v1[brev5(b)] = row[33 * (tq + 16) + b];
+    }
+    __syncthreads();
+    if (has0) {
+        radixR<LAZY, 5>(v0, md, rt);
+#pragma unroll
+        for (int k0 = 0; k0 < 32; ++k0) row[padi(tq + RA * k0)] = v0[k0];
+    }
+    if (has1) {
+        radixR<LAZY, 5>(v1, md, rt);
+#pragma unroll
+        for (int k0 = 0; k0 < 32; ++k0) row[padi(tq + 16 + RA * k0)] = v1[k0];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileW * N; e += kFastThreads) {
+        const int ww = e >> LOG_N, i = e & (N - 1);
+        if ((size_t)ww < rows_here) {
+            uint32_t val = tile[ww * kRowStride + padi(i)];
+            if (scale != 1u) {
+                val = md.mul(val, scale, scale_sh);
+                if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
+            } else {
+                val = md.canon(val);
+            }
+            dst[e] = (T)val;
+        }
     }
 }
 
@@ -342,17 +444,23 @@ __global__ void __launch_bounds__(kFastThreads, 2)
 // 74 * 64 CTAs = 16 full waves of 2 CTAs/SM x 148 SMs
 static size_t fast_chunk(const gfb_ntt_plan* pl) { return (size_t)kNttChunk << (20 - pl->log_n); }
 
-template <typename T, bool LAZY, int LOG_RA>
-static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
-    Mod<LAZY> md{pl->p, pl->p * 2u};
+static Radix32Roots roots_of(const gfb_ntt_plan* pl) {
     Radix32Roots rt;
     memcpy(rt.w, pl->rho, sizeof(rt.w));
     memcpy(rt.ws, pl->rho_sh, sizeof(rt.ws));
+    return rt;
+}
+
+// N = n1 x 1024, n1 = 32 RA (2^15 .. 2^20)
+template <typename T, bool LAZY, int LOG_RA>
+static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    Mod<LAZY> md{pl->p, pl->p * 2u};
+    const Radix32Roots rt = roots_of(pl);
     static bool attr_set = false;
     if (!attr_set) {
         GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kFastSmem));
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kFastSmem));
         attr_set = true;
     }
@@ -364,22 +472,76 @@ static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, 
         T* yout = y + (off << pl->log_n);
         k_ntt_pass1<T, LAZY, LOG_RA>
             <<<(unsigned)(cnt * 64), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt1, pl->d_tw4, xin, ws);
-        k_ntt_pass2<T, LAZY><<<(unsigned)(cnt << (log_n1 - 4)), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, ws, yout,
-                                                                                             log_n1);
+        k_ntt_pass2<T, LAZY, false><<<(unsigned)(cnt << (log_n1 - 4)), kFastThreads, kFastSmem, st>>>(
+            md, rt, pl->d_zt, ws, yout, log_n1, cnt << log_n1);
     }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+// N = n1 x 1024, n1 = 2 .. 16 (2^11 .. 2^14)
+template <typename T, bool LAZY, int LOG_N1>
+static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    Mod<LAZY> md{pl->p, pl->p * 2u};
+    const Radix32Roots rt = roots_of(pl);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kFastSmem));
+        attr_set = true;
+    }
+    const size_t chunk = fast_chunk(pl);
+    for (size_t off = 0; off < batch; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        const T* xin = x + (off << pl->log_n);
+        T* yout = y + (off << pl->log_n);
+        const size_t columns = cnt << 10, rows = cnt << LOG_N1;
+        k_ntt_pass1_small<T, LAZY, LOG_N1><<<(unsigned)((columns + 255) / 256), 256, 0, st>>>(md, rt, pl->d_tw4, xin, ws,
+                                                                                               columns);
+        k_ntt_pass2<T, LAZY, true><<<(unsigned)((rows + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
+            md, rt, pl->d_zt, ws, yout, LOG_N1, rows);
+    }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+// N = 32 RA <= 1024: one kernel
+template <typename T, bool LAZY, int LOG_RA>
+static gfb_status run_small_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, cudaStream_t st) {
+    Mod<LAZY> md{pl->p, pl->p * 2u};
+    const Radix32Roots rt = roots_of(pl);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_small<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kFastSmem));
+        attr_set = true;
+    }
+    const uint32_t scale_sh = (uint32_t)((((unsigned long long)pl->scale) << 32) / pl->p);
+    k_ntt_small<T, LAZY, LOG_RA><<<(unsigned)((batch + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
+        md, rt, pl->d_zt, x, y, batch, pl->scale, scale_sh);
     GFB_CUDA_TRY(cudaGetLastError());
     return GFB_OK;
 }
 
 template <typename T, bool LAZY>
 static gfb_status run_fast_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
-    switch (pl->log_n - 15) {
-        case 0: return run_fast_ra<T, LAZY, 0>(pl, x, y, batch, ws, st);
-        case 1: return run_fast_ra<T, LAZY, 1>(pl, x, y, batch, ws, st);
-        case 2: return run_fast_ra<T, LAZY, 2>(pl, x, y, batch, ws, st);
-        case 3: return run_fast_ra<T, LAZY, 3>(pl, x, y, batch, ws, st);
-        case 4: return run_fast_ra<T, LAZY, 4>(pl, x, y, batch, ws, st);
-        case 5: return run_fast_ra<T, LAZY, 5>(pl, x, y, batch, ws, st);
+    switch (pl->log_n) {
+        case 5: return run_small_ra<T, LAZY, 0>(pl, x, y, batch, st);
+        case 6: return run_small_ra<T, LAZY, 1>(pl, x, y, batch, st);
+        case 7: return run_small_ra<T, LAZY, 2>(pl, x, y, batch, st);
+        case 8: return run_small_ra<T, LAZY, 3>(pl, x, y, batch, st);
+        case 9: return run_small_ra<T, LAZY, 4>(pl, x, y, batch, st);
+        case 10: return run_small_ra<T, LAZY, 5>(pl, x, y, batch, st);
+        case 11: return run_fast_short<T, LAZY, 1>(pl, x, y, batch, ws, st);
+        case 12: return run_fast_short<T, LAZY, 2>(pl, x, y, batch, ws, st);
+        case 13: return run_fast_short<T, LAZY, 3>(pl, x, y, batch, ws, st);
+        case 14: return run_fast_short<T, LAZY, 4>(pl, x, y, batch, ws, st);
+        case 15: return run_fast_ra<T, LAZY, 0>(pl, x, y, batch, ws, st);
+        case 16: return run_fast_ra<T, LAZY, 1>(pl, x, y, batch, ws, st);
+        case 17: return run_fast_ra<T, LAZY, 2>(pl, x, y, batch, ws, st);
+        case 18: return run_fast_ra<T, LAZY, 3>(pl, x, y, batch, ws, st);
+        case 19: return run_fast_ra<T, LAZY, 4>(pl, x, y, batch, ws, st);
+        case 20: return run_fast_ra<T, LAZY, 5>(pl, x, y, batch, ws, st);
     }
     return GFB_ERR_BAD_ARG;
 }
@@ -463,7 +625,7 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
     pl->p = p;
     pl->omega = (uint32_t)omega;
     pl->scale = (uint32_t)scale;
-    pl->fast = pl->log_n >= 15 && pl->log_n <= 20 && p < (1u << 31);
+    pl->fast = pl->log_n >= 5 && pl->log_n <= 20 && p < (1u << 31);
     pl->lazy = p < (1u << 30);
     PrimeBarrett fb = f->prime_barrett();
     const size_t npow = n / 2 ? n / 2 : 1;
@@ -475,24 +637,34 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
             e = cudaGetLastError();
         }
     } else {
-        // N = n1 x 1024: zeta1 = omega^1024 has order n1 (column transforms), zeta2 = omega^n1 has order 1024 (row
-        // transforms), rho = omega^(N/32) is the 32nd root shared by every in-register radix stage
-        const size_t n1 = n >> 10;
-        const uint32_t zeta1 = host_powmod(pl->omega, 1024, p);
-        const uint32_t zeta2 = host_powmod(pl->omega, n1, p);
+        // rho = omega^(N/32) is the 32nd root shared by every in-register radix stage
         const uint32_t rho = host_powmod(pl->omega, n / 32, p);
         for (int i = 0; i < 16; ++i) {
             pl->rho[i] = host_powmod(rho, i, p);
             pl->rho_sh[i] = (uint32_t)((((unsigned long long)pl->rho[i]) << 32) / p);
         }
-        e = cudaMalloc((void**)&pl->d_tw4, n * sizeof(uint2));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt, 1024 * sizeof(uint2));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt1, n1 * sizeof(uint2));
-        if (e == cudaSuccess) {
-            k_build_tw4<<<(unsigned)((n + 255) / 256), 256>>>(fb, pl->omega, pl->scale, pl->d_tw4, n);
-            k_build_zt<<<4, 256>>>(fb, zeta2, pl->d_zt, 1024);
-            k_build_zt<<<(unsigned)((n1 + 255) / 256), 256>>>(fb, zeta1, pl->d_zt1, (int)n1);
-            e = cudaGetLastError();
+        if (pl->log_n <= 10) {
+            // single kernel, N = 32 RA: zt[k1*32 + t] = omega^(t k1), k1 < RA
+            e = cudaMalloc((void**)&pl->d_zt, n * sizeof(uint2));
+            if (e == cudaSuccess) {
+                k_build_zt<<<(unsigned)((n + 255) / 256), 256>>>(fb, pl->omega, pl->d_zt, (int)n);
+                e = cudaGetLastError();
+            }
+        } else {
+            // N = n1 x 1024: zeta1 = omega^1024 has order n1 (column transforms, needed when n1 >= 32),
+            // zeta2 = omega^n1 has order 1024 (row transforms)
+            const size_t n1 = n >> 10;
+            const uint32_t zeta1 = host_powmod(pl->omega, 1024, p);
+            const uint32_t zeta2 = host_powmod(pl->omega, n1, p);
+            e = cudaMalloc((void**)&pl->d_tw4, n * sizeof(uint2));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_zt, 1024 * sizeof(uint2));
+            if (e == cudaSuccess && n1 >= 32) e = cudaMalloc((void**)&pl->d_zt1, n1 * sizeof(uint2));
+            if (e == cudaSuccess) {
+                k_build_tw4<<<(unsigned)((n + 255) / 256), 256>>>(fb, pl->omega, pl->scale, pl->d_tw4, n);
+                k_build_zt<<<4, 256>>>(fb, zeta2, pl->d_zt, 1024);
+                if (n1 >= 32) k_build_zt<<<(unsigned)((n1 + 255) / 256), 256>>>(fb, zeta1, pl->d_zt1, (int)n1);
+                e = cudaGetLastError();
+            }
         }
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -519,6 +691,7 @@ size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t ba
     (void)elem_bytes;
     if (!pl || batch == 0) return 0;
     if (pl->fast) {
+        if (pl->log_n <= 10) return 0;  // single kernel
         const size_t chunk = fast_chunk(pl);
         const size_t rows = batch < chunk ? batch : chunk;
         return rows * pl->n * sizeof(uint32_t);

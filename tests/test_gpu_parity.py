@@ -539,3 +539,25 @@ def test_ntt_four_step_sizes(log_n):
             assert np.array_equal(np.asarray(gb.intt(X)), np.asarray(x)), (log_n, p, dtype)
         d = x.to_device()
         assert np.array_equal(np.asarray(gb.ntt_device(gb.ntt_device(d), inverse=True).cpu()), np.asarray(x))
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)))
+def test_ntt_small_sizes(log_n):
+    """N = 1 .. 2^14: generic Stockham path (N < 32), single-kernel path (32 .. 1024) and short-column four-step
+    (2^11 .. 2^14) vs the oracle, with batch sizes that are not multiples of the 16-transform tile."""
+    n = 1 << log_n
+    for p in (998244353, 2013265921, 7340033):
+        if (p - 1) % n:
+            continue
+        GF = gb.GF(p)
+        F = oracle.Field.prime(p)
+        omega = int(GF.primitive_root_of_unity(n)) if n > 1 else 1
+        for rows in (1, 5, 16, 37):
+            x = GF.Random((rows, n), seed=100 + log_n + rows)
+            X = gb.ntt(x)
+            assert np.array_equal(np.asarray(X).astype(np.int64), F.fft(np.asarray(x), omega)), (log_n, p, rows)
+            assert np.array_equal(np.asarray(gb.intt(X)), np.asarray(x)), (log_n, p, rows)
+        x64 = GF.Random((3, n), seed=7, dtype=np.int64)
+        assert np.array_equal(np.asarray(gb.ntt(x64)).astype(np.int64), F.fft(np.asarray(x64), omega))
+        assert np.array_equal(np.asarray(gb.intt(x64, scaled=False)).astype(np.int64),
+                              F.fft(np.asarray(x64), pow(omega, -1, p)))
