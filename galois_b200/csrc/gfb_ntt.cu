@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(256)
     const size_t transform = col >> 10, c = col & 1023;
     const T* src = x + (transform << (LOG_N1 + 10)) + c;
     uint32_t* dst = ws + (transform << (LOG_N1 + 10)) + c;
+    static_assert(LOG_N1 <= 5, "one in-register radix stage set covers at most 32 points");
     uint32_t v[N1];
 #pragma unroll
     for (int r = 0; r < N1; ++r) v[brev<LOG_N1>(r)] = (uint32_t)__ldcs(src + (size_t)r * 1024);
@@ -365,6 +366,46 @@ __global__ void __launch_bounds__(256)
         uint32_t val = md.mul(v[k], tw.x, tw.y);
         if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
         dst[(size_t)k * 1024] = val;
+    }
+}
+
+// pass 1 for n1 = 64 (N = 2^16): still one thread per column — a radix-2 step across the two 32-row halves, the
+// zeta1^(i0) twiddle, then two in-register radix-32 transforms (X[k1 + 2 k0], k1 in {0,1}).
+template <typename T, bool LAZY>
+__global__ void __launch_bounds__(256)
+    k_ntt_pass1_c64(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt1, const uint2* __restrict__ tw4,
+                    const T* __restrict__ x, uint32_t* __restrict__ ws, size_t columns_total) {
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= columns_total) return;
+    const size_t transform = col >> 10, c = col & 1023;
+    const T* src = x + (transform << 16) + c;
+    uint32_t* dst = ws + (transform << 16) + c;
+    uint32_t a0[32], a1[32];
+#pragma unroll
+    for (int i0 = 0; i0 < 32; ++i0) {
+        a0[brev5(i0)] = (uint32_t)__ldcs(src + (size_t)i0 * 1024);
+        a1[brev5(i0)] = (uint32_t)__ldcs(src + (size_t)(32 + i0) * 1024);
+    }
+#pragma unroll
+    for (int i0 = 0; i0 < 32; ++i0) {
+        md.bfly1(a0[brev5(i0)], a1[brev5(i0)]);  // Y[0][i0], Y[1][i0]
+        if (i0 > 0) {
+            const uint2 z = __ldg(&zt1[32 + i0]);  // zeta1^(i0 * 1)
+            a1[brev5(i0)] = md.mul(a1[brev5(i0)], z.x, z.y);
+        }
+    }
+    radixR<LAZY, 5>(a0, md, rt);
+    radixR<LAZY, 5>(a1, md, rt);
+#pragma unroll
+    for (int k0 = 0; k0 < 32; ++k0) {
+#pragma unroll
+        for (int k1 = 0; k1 < 2; ++k1) {
+            const size_t k = (size_t)(k1 + 2 * k0);
+            const uint2 tw = __ldg(tw4 + k * 1024 + c);
+            uint32_t val = md.mul(k1 ? a1[k0] : a0[k0], tw.x, tw.y);
+            if constexpr (LAZY) val = Mod<LAZY>::csub(val, md.p);
+            dst[k * 1024] = val;
+        }
     }
 }
 
@@ -479,15 +520,15 @@ static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, 
     return GFB_OK;
 }
 
-// N = n1 x 1024, n1 = 2 .. 16 (2^11 .. 2^14)
+// N = n1 x 1024, n1 = 2 .. 64 (2^11 .. 2^16): columns short enough for one thread each
 template <typename T, bool LAZY, int LOG_N1>
 static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
     Mod<LAZY> md{pl->p, pl->p * 2u};
     const Radix32Roots rt = roots_of(pl);
     static bool attr_set = false;
     if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kFastSmem));
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, (LOG_N1 < 4)>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         attr_set = true;
     }
     const size_t chunk = fast_chunk(pl);
@@ -496,9 +537,13 @@ static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batc
         const T* xin = x + (off << pl->log_n);
         T* yout = y + (off << pl->log_n);
         const size_t columns = cnt << 10, rows = cnt << LOG_N1;
-        k_ntt_pass1_small<T, LAZY, LOG_N1><<<(unsigned)((columns + 255) / 256), 256, 0, st>>>(md, rt, pl->d_tw4, xin, ws,
-                                                                                               columns);
-        k_ntt_pass2<T, LAZY, true><<<(unsigned)((rows + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
+        if constexpr (LOG_N1 == 6)
+            k_ntt_pass1_c64<T, LAZY><<<(unsigned)((columns + 255) / 256), 256, 0, st>>>(md, rt, pl->d_zt1, pl->d_tw4, xin,
+                                                                                        ws, columns);
+        else
+            k_ntt_pass1_small<T, LAZY, LOG_N1><<<(unsigned)((columns + 255) / 256), 256, 0, st>>>(md, rt, pl->d_tw4, xin,
+                                                                                                   ws, columns);
+        k_ntt_pass2<T, LAZY, (LOG_N1 < 4)><<<(unsigned)((rows + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
             md, rt, pl->d_zt, ws, yout, LOG_N1, rows);
     }
     GFB_CUDA_TRY(cudaGetLastError());
@@ -536,8 +581,8 @@ static gfb_status run_fast_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, u
         case 12: return run_fast_short<T, LAZY, 2>(pl, x, y, batch, ws, st);
         case 13: return run_fast_short<T, LAZY, 3>(pl, x, y, batch, ws, st);
         case 14: return run_fast_short<T, LAZY, 4>(pl, x, y, batch, ws, st);
-        case 15: return run_fast_ra<T, LAZY, 0>(pl, x, y, batch, ws, st);
-        case 16: return run_fast_ra<T, LAZY, 1>(pl, x, y, batch, ws, st);
+        case 15: return run_fast_short<T, LAZY, 5>(pl, x, y, batch, ws, st);
+        case 16: return run_fast_short<T, LAZY, 6>(pl, x, y, batch, ws, st);
         case 17: return run_fast_ra<T, LAZY, 2>(pl, x, y, batch, ws, st);
         case 18: return run_fast_ra<T, LAZY, 3>(pl, x, y, batch, ws, st);
         case 19: return run_fast_ra<T, LAZY, 4>(pl, x, y, batch, ws, st);
