@@ -288,11 +288,13 @@ __global__ void __launch_bounds__(kFastThreads, 2)
 // pass 2: the n1 row NTTs of length 1024 + transposed store.  One CTA per (transform, 16-row tile).  The 16 rows are
 // contiguous in the workspace, so they are staged through the tile (coalesced along the row, transposed by the tile
 // layout); the outputs X[k1 + n1 k2] have the 16 rows (k1) innermost and go straight from registers to global memory.
-template <typename T, bool LAZY, bool SMALL>
+template <typename T, bool LAZY, bool SMALL, int LOG_N1_CT>
 __global__ void __launch_bounds__(kFastThreads, 2)
     k_ntt_pass2(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint32_t* __restrict__ ws,
-                T* __restrict__ y, int log_n1, size_t rows_total) {
+                T* __restrict__ y, int log_n1_rt, size_t rows_total) {
     extern __shared__ uint32_t tile[];
+    // compile-time n1 for the large sizes keeps the 32 transposed stores on immediate offsets (no 64-bit IMADs)
+    const int log_n1 = LOG_N1_CT >= 0 ? LOG_N1_CT : log_n1_rt;
     // the workspace is [transform][k1 < n1][1024]: rows are contiguous across transforms, a tile is 16 consecutive rows
     const size_t row0 = (size_t)blockIdx.x * kTileW;
     const size_t n1 = (size_t)1 << log_n1;
@@ -501,8 +503,8 @@ static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, 
     if (!attr_set) {
         GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kFastSmem));
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kFastSmem));
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, false, LOG_RA + 5>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         attr_set = true;
     }
     const int log_n1 = LOG_RA + 5;
@@ -513,7 +515,7 @@ static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, 
         T* yout = y + (off << pl->log_n);
         k_ntt_pass1<T, LAZY, LOG_RA>
             <<<(unsigned)(cnt * 64), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt1, pl->d_tw4, xin, ws);
-        k_ntt_pass2<T, LAZY, false><<<(unsigned)(cnt << (log_n1 - 4)), kFastThreads, kFastSmem, st>>>(
+        k_ntt_pass2<T, LAZY, false, LOG_RA + 5><<<(unsigned)(cnt << (log_n1 - 4)), kFastThreads, kFastSmem, st>>>(
             md, rt, pl->d_zt, ws, yout, log_n1, cnt << log_n1);
     }
     GFB_CUDA_TRY(cudaGetLastError());
@@ -527,7 +529,7 @@ static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batc
     const Radix32Roots rt = roots_of(pl);
     static bool attr_set = false;
     if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, (LOG_N1 < 4)>,
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, (LOG_N1 < 4), LOG_N1>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
         attr_set = true;
     }
@@ -543,8 +545,9 @@ static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batc
         else
             k_ntt_pass1_small<T, LAZY, LOG_N1><<<(unsigned)((columns + 255) / 256), 256, 0, st>>>(md, rt, pl->d_tw4, xin,
                                                                                                    ws, columns);
-        k_ntt_pass2<T, LAZY, (LOG_N1 < 4)><<<(unsigned)((rows + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
-            md, rt, pl->d_zt, ws, yout, LOG_N1, rows);
+        k_ntt_pass2<T, LAZY, (LOG_N1 < 4), LOG_N1>
+            <<<(unsigned)((rows + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(md, rt, pl->d_zt, ws, yout, LOG_N1,
+                                                                                        rows);
     }
     GFB_CUDA_TRY(cudaGetLastError());
     return GFB_OK;
