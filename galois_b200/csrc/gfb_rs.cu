@@ -138,6 +138,79 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v) {
     return v;
 }
 
+// Berlekamp-Massey with the polynomials held in registers: coefficient i lives in lane i % 32, register i / 32.
+// Same state machine as berlekamp_massey_jit.implementation (_lfsr.py:1647-1702) on arrays of S.size = ls entries:
+//   C   connection polynomial,  Bs = x^m * B (the reference keeps B and the shift count m separately; multiplying by x
+//   once per iteration is the same thing),  Sw[i] = S[n - i] (a window sliding one lane per iteration).
+// Writes Λ = C[:L+1] with high-degree zeros trimmed to lam[] (ascending) and returns its length.
+template <int NR>
+__device__ __forceinline__ int bm_registers(const Gf8& gf, const uint8_t* Sq, int ls, uint8_t* lam, int lane) {
+    uint32_t Cr[NR], Bs[NR], Sw[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        Cr[r] = (r == 0 && lane == 0) ? 1u : 0u;
+        Bs[r] = (r == 0 && lane == 1) ? 1u : 0u;  // x^1 * B, B = 1
+        Sw[r] = 0u;
+    }
+    // y <- x * y : shift every coefficient one index up, `fill` enters at index 0
+    auto shift_up = [&](uint32_t (&y)[NR], uint32_t fill) {
+#pragma unroll
+        for (int r = NR - 1; r >= 0; --r) {
+            const uint32_t below = __shfl_up_sync(0xffffffffu, y[r], 1);
+            const uint32_t carry = r > 0 ? __shfl_sync(0xffffffffu, y[r > 0 ? r - 1 : 0], 31) : fill;
+            y[r] = lane == 0 ? carry : below;
+        }
+    };
+    int L = 0;
+    uint32_t b = 1;
+    for (int nn = 0; nn < ls; ++nn) {
+        shift_up(Sw, (uint32_t)Sq[nn]);
+        uint32_t dsc = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (lane + 32 * r <= L) dsc ^= gf.mul(Sw[r], Cr[r]);
+        dsc = warp_xor(dsc);
+        if (dsc == 0) {
+            shift_up(Bs, 0u);  // m += 1
+        } else {
+            const uint32_t dob = gf.mul(dsc, gf.inv(b));
+            if (2 * L > nn) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r)
+                    if (lane + 32 * r < ls) Cr[r] ^= gf.mul(dob, Bs[r]);
+                shift_up(Bs, 0u);  // m += 1
+            } else {
+                uint32_t Tr[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    Tr[r] = Cr[r];
+                    if (lane + 32 * r < ls) Cr[r] ^= gf.mul(dob, Bs[r]);
+                }
+                L = nn + 1 - L;
+                b = dsc;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) Bs[r] = Tr[r];
+                shift_up(Bs, 0u);  // B = T, m = 1
+            }
+        }
+    }
+    const int len = L + 1 < ls ? L + 1 : ls;
+    int last = -1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+        if (lane + 32 * r < len && Cr[r] != 0) last = lane + 32 * r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, last, o);
+        last = other > last ? other : last;
+    }
+    const int lam_len = last >= 0 ? last + 1 : 1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+        if (lane + 32 * r < lam_len) lam[lane + 32 * r] = (uint8_t)Cr[r];
+    return lam_len;
+}
+
 __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_t* __restrict__ received,
                                                            const uint8_t* __restrict__ erasures, int ns,
                                                            uint8_t* __restrict__ decoded, long long* __restrict__ n_errors,
@@ -252,54 +325,19 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
                 Sp[l] = (uint8_t)acc;
             }
             __syncwarp();
-            // ---- 4. Berlekamp-Massey on S'[u:] (:1421-1428; _lfsr.py:1647-1702)
+            // ---- 4. Berlekamp-Massey on S'[u:] (:1421-1428; _lfsr.py:1647-1702), register-resident
             int lam_len = 1;
             if (u < d1) {
                 const uint8_t* Sq = Sp + u;
                 const int ls = d1 - u;  // S.size
-                for (int i = lane; i < ls; i += 32) {
-                    C[i] = (i == 0);
-                    B[i] = (i == 0);
-                }
-                __syncwarp();
-                int L = 0, mm = 1;
-                uint32_t b = 1;
-                for (int nn = 0; nn < ls; ++nn) {
-                    uint32_t dsc = 0;
-                    for (int i = lane; i <= L; i += 32) dsc ^= gf.mul(Sq[nn - i], C[i]);
-                    dsc = warp_xor(dsc);
-                    if (dsc == 0) {
-                        mm += 1;
-                    } else {
-                        const uint32_t dob = gf.mul(dsc, gf.inv(b));
-                        if (2 * L > nn) {
-                            for (int i = mm + lane; i < ls; i += 32) C[i] ^= (uint8_t)gf.mul(dob, B[i - mm]);
-                            mm += 1;
-                        } else {
-                            for (int i = lane; i < ls; i += 32) T[i] = C[i];
-                            __syncwarp();
-                            for (int i = mm + lane; i < ls; i += 32) C[i] ^= (uint8_t)gf.mul(dob, B[i - mm]);
-                            __syncwarp();
-                            for (int i = lane; i < ls; i += 32) B[i] = T[i];
-                            L = nn + 1 - L;
-                            b = dsc;
-                            mm = 1;
-                        }
-                    }
-                    __syncwarp();
-                }
-                // C = C[:L+1], trim high-degree zeros; Λ ascending = C
-                int len = L + 1 < ls ? L + 1 : ls;
-                int last = -1;
-                for (int i = lane; i < len; i += 32)
-                    if (C[i] != 0) last = i;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    int other = __shfl_xor_sync(0xffffffffu, last, o);
-                    last = other > last ? other : last;
-                }
-                lam_len = last >= 0 ? last + 1 : 1;
-                for (int i = lane; i < lam_len; i += 32) lam[i] = C[i];
+                if (ls <= 32)
+                    lam_len = bm_registers<1>(gf, Sq, ls, lam, lane);
+                else if (ls <= 64)
+                    lam_len = bm_registers<2>(gf, Sq, ls, lam, lane);
+                else if (ls <= 128)
+                    lam_len = bm_registers<4>(gf, Sq, ls, lam, lane);
+                else
+                    lam_len = bm_registers<8>(gf, Sq, ls, lam, lane);
             } else {
                 if (lane == 0) lam[0] = 1;
             }

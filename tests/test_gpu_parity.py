@@ -561,3 +561,33 @@ def test_ntt_small_sizes(log_n):
         assert np.array_equal(np.asarray(gb.ntt(x64)).astype(np.int64), F.fft(np.asarray(x64), omega))
         assert np.array_equal(np.asarray(gb.intt(x64, scaled=False)).astype(np.int64),
                               F.fft(np.asarray(x64), pow(omega, -1, p)))
+
+
+@pytest.mark.parametrize(["n", "k"], [(255, 155), (255, 101), (255, 5), (63, 3)])
+def test_rs_low_rate_codes_vs_oracle(n, k):
+    """Low-rate codes: d - 1 = 100 .. 250 syndromes exercise the multi-register Berlekamp-Massey (4 and 8 coefficients
+    per lane) and long erasure locators; errors, erasures, mixtures and failures vs the oracle."""
+    m = 8 if n == 255 else 6
+    poly = {8: 0x11D, 6: 0x43}[m]
+    rs = gb.ReedSolomon(n, k)
+    assert int(rs.field.irreducible_poly) == poly
+    F = oracle.Field.binary(m, poly, alpha=2)
+    ors = oracle.ReedSolomon(F, n, k)
+    d1 = n - k
+    rng = np.random.default_rng(n * 1000 + k)
+    N = 300
+    M = rs.field.Random((N, k), seed=k)
+    C = np.asarray(rs.encode(M))
+    assert np.array_equal(C, ors.encode(np.asarray(M)))
+    for n_err, n_era in [(d1 // 2, 0), (0, d1), (d1 // 4, d1 - 2 * (d1 // 4)), (d1 // 2 + 1, 0), (1, d1), (3, 5)]:
+        R = C.copy()
+        E = np.zeros(R.shape, dtype=bool)
+        for i in range(N):
+            pos = rng.choice(n, min(n, n_err + n_era), replace=False)
+            R[i, pos[:n_err]] ^= rng.integers(1, 1 << m, len(pos[:n_err])).astype(np.uint8)
+            E[i, pos[n_err:]] = True
+            R[i, pos[n_err:]] = rng.integers(0, 1 << m, len(pos[n_err:]))
+        dec, nerr = rs.decode(R, erasures=E if n_era else None, output="codeword", errors=True)
+        odec, onerr = ors.decode(R, E if n_era else None, threads=8)
+        assert np.array_equal(nerr, onerr), (n, k, n_err, n_era)
+        assert np.array_equal(np.asarray(dec), odec), (n, k, n_err, n_era)
