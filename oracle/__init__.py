@@ -227,6 +227,130 @@ class Field:
         return out[:n]
 
 
+    # ---------------------------------------------------------------- polynomial roots
+    def poly_roots(self, nonzero_degrees, nonzero_coeffs, primitive_element: int | None = None) -> np.ndarray:
+        """roots_jit.__call__ (_polys/_dense.py:448-466): Chien search, then the roots in increasing order."""
+        d, c = _i64(nonzero_degrees), _i64(nonzero_coeffs)
+        alpha = self.alpha if primitive_element is None else primitive_element
+        cap = int(min(max(int(d.max()), 1) + 2, self.order))
+        if not c.any():
+            cap = self.order  # the zero polynomial: every power of alpha passes the test
+        roots = np.zeros(cap, dtype=np.int64)
+        powers = np.zeros(cap, dtype=np.int64)
+        lib().orc_poly_roots.restype = ctypes.c_int64
+        n = lib().orc_poly_roots(
+            self.ref, _ptr(d), _ptr(c), ctypes.c_int64(d.size), ctypes.c_int64(alpha), _ptr(roots), _ptr(powers)
+        )
+        return np.sort(roots[:n])
+
+    # ---------------------------------------------------------------- dense linear algebra
+    def row_reduce(self, A, ncols: int | None = None):
+        """row_reduce_jit.__call__ (_domains/_linalg.py:321-353) -> (A_rre, n_pivots)."""
+        A = _i64(A).copy()
+        rows, cols = A.shape
+        ncols = cols if ncols is None else ncols
+        lib().orc_row_reduce.restype = ctypes.c_int64
+        p = lib().orc_row_reduce(self.ref, _ptr(A), ctypes.c_int64(rows), ctypes.c_int64(cols), ctypes.c_int64(ncols))
+        return A, int(p)
+
+    def plu_decompose(self, A):
+        """plu_decompose_jit.__call__ (_linalg.py:390-428) -> (P, L, U, n_permutations) with A = P L U."""
+        U = _i64(A).copy()
+        m, n = U.shape
+        L = np.zeros((m, m), dtype=np.int64)
+        perm = np.zeros(m, dtype=np.int64)
+        lib().orc_plu_decompose.restype = ctypes.c_int64
+        n_perm = lib().orc_plu_decompose(self.ref, _ptr(U), _ptr(L), _ptr(perm), ctypes.c_int64(m), ctypes.c_int64(n))
+        P_rows = np.zeros((m, m), dtype=np.int64)  # the reference's row-swapped identity
+        P_rows[np.arange(m), perm] = 1
+        return P_rows.T.copy(), L, U, int(n_perm)
+
+    def lu_decompose(self, A):
+        """lu_decompose_jit.__call__ (_linalg.py:356-387) -> (L, U); ValueError when a row swap would be needed."""
+        U = _i64(A).copy()
+        m, n = U.shape
+        L = np.zeros((m, m), dtype=np.int64)
+        rc = lib().orc_lu_decompose(self.ref, _ptr(U), _ptr(L), ctypes.c_int64(m), ctypes.c_int64(n))
+        if rc:
+            raise ValueError("The LU decomposition of 'A' does not exist. Use the PLU decomposition instead.")
+        return L, U
+
+    def matrix_rank(self, A) -> int:
+        """matrix_rank_jit (_linalg.py:479-489)."""
+        R, _ = self.row_reduce(A)
+        return int(np.sum(~np.all(R == 0, axis=1)))
+
+    def row_reduce_eye(self, A, ncols: int | None = None, eye: str = "left"):
+        """FieldArray.row_reduce (_fields/_array.py:1412-1469): eye="right" reduces the doubly-reversed matrix."""
+        A = _i64(A)
+        if eye == "left":
+            return self.row_reduce(A, ncols)[0]
+        return self.row_reduce(A[::-1, ::-1], ncols)[0][::-1, ::-1].copy()
+
+    def row_space(self, A):
+        """FieldArray.row_space (_fields/_array.py:1541-1590)."""
+        R, _ = self.row_reduce(A)
+        rank = int(np.sum(~np.all(R == 0, axis=1)))
+        return R[:rank, :]
+
+    def column_space(self, A):
+        return self.row_space(_i64(A).T)
+
+    def left_null_space(self, A):
+        """FieldArray.left_null_space (_fields/_array.py:1639-1703)."""
+        A = _i64(A)
+        m, n = A.shape
+        AI = np.concatenate([A, np.eye(m, dtype=np.int64)], axis=-1)
+        R, p = self.row_reduce(AI, ncols=n)
+        LN = R[p:, n:]
+        if LN.shape[0] == 0:
+            return LN.copy()
+        return self.row_reduce(LN)[0]
+
+    def null_space(self, A):
+        return self.left_null_space(_i64(A).T)
+
+    def matrix_inv(self, A):
+        """inv_jit (_linalg.py:492-522): row-reduce [A | I] on the first n columns."""
+        A = _i64(A)
+        n = A.shape[0]
+        AI = np.concatenate([A, np.eye(n, dtype=np.int64)], axis=-1)
+        R, _ = self.row_reduce(AI, ncols=n)
+        rank = int(np.sum(~np.all(R[:, :n] == 0, axis=1)))
+        if rank != n:
+            raise np.linalg.LinAlgError(
+                f"Argument 'A' is singular and not invertible because it does not have full rank of {n}, "
+                f"but rank of {rank}."
+            )
+        return R[:, -n:].copy()
+
+    def solve(self, A, b):
+        """solve_jit (_linalg.py:525-546): x = A^-1 b."""
+        b = _i64(b)
+        Ainv = self.matrix_inv(A)
+        if b.ndim == 1:
+            return self.matmul(Ainv, b.reshape(-1, 1)).reshape(-1)
+        return self.matmul(Ainv, b)
+
+    def det(self, A) -> int:
+        """det_jit (_linalg.py:446-471): closed forms for n = 2, 3, otherwise (-1)^swaps det(L) det(U)."""
+        A = _i64(A)
+        n = A.shape[0]
+        mul, sub = (lambda x, y: int(self.mul(x, y).item())), (lambda x, y: int(self.sub(x, y).item()))
+        if n == 2:
+            return sub(mul(A[0, 0], A[1, 1]), mul(A[0, 1], A[1, 0]))
+        if n == 3:
+            t0 = mul(A[0, 0], sub(mul(A[1, 1], A[2, 2]), mul(A[1, 2], A[2, 1])))
+            t1 = mul(A[0, 1], sub(mul(A[1, 0], A[2, 2]), mul(A[1, 2], A[2, 0])))
+            t2 = mul(A[0, 2], sub(mul(A[1, 0], A[2, 1]), mul(A[1, 1], A[2, 0])))
+            return int(self.add(sub(t0, t1), t2).item())
+        _, L, U, n_perm = self.plu_decompose(A)
+        det = 1
+        for i in range(n):
+            det = mul(det, mul(L[i, i], U[i, i]))
+        return int(self.neg(det).item()) if n_perm % 2 else det
+
+
 def prime_factors(n: int) -> list[int]:
     """Prime factors with multiplicity, ascending (fft_jit._prime_factors, _function.py:214-229)."""
     out, d = [], 2

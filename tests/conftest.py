@@ -65,3 +65,18 @@ def ref_bch():
 @pytest.fixture(scope="session")
 def live_bch():
     return _load("live_bch.npz"), json.load(open(GOLDEN / "live_bch_meta.json"))
+
+
+@pytest.fixture(scope="session")
+def ref_linalg():
+    return _load("ref_linalg.npz")
+
+
+@pytest.fixture(scope="session")
+def ref_roots():
+    return _load("ref_roots.npz")
+
+
+@pytest.fixture(scope="session")
+def live_next():
+    return _load("live_next.npz"), json.load(open(GOLDEN / "live_next_meta.json"))

@@ -481,8 +481,151 @@ def live_bch():
     print("live_bch.npz", len(out), "arrays")
 
 
+
+# --------------------------------------------------------------------------- §8(f) rows: roots, mixed-radix FFT, dense linalg
+LINALG_FIELDS = ["GF(2)", "GF(2^2)", "GF(2^3)", "GF(2^8)", "GF(2^32)", "GF(5)", "GF(7)", "GF(31)", "GF(3191)",
+                 "GF(2147483647)"]
+
+
+def convert_linalg_vectors():
+    """Sage vectors for row_reduce / lu / plu / inv / det / solve / row, column and null spaces (tests/fields/data)."""
+    ops = {"row_reduce": ("X", "Z"), "lu_decompose": ("X", "L", "U"), "plu_decompose": ("X", "P", "L", "U"),
+           "matrix_inverse": ("X", "Z"), "matrix_determinant": ("X", "Z"), "matrix_solve": ("X", "Y", "Z"),
+           "row_space": ("X", "Z"), "column_space": ("X", "Z"), "left_null_space": ("X", "Z"), "null_space": ("X", "Z")}
+    out = {}
+    for fld in LINALG_FIELDS:
+        folder = REF / "tests" / "fields" / "data" / fld
+        for op, keys in ops.items():
+            d = pickle.load(open(folder / f"{op}.pkl", "rb"))
+            out[f"{fld}/{op}/count"] = np.array(len(d[keys[0]]))
+            for key in keys:
+                for i, item in enumerate(d[key]):
+                    out[f"{fld}/{op}/{key}{i}"] = np.asarray(item).astype(np.int64)
+    np.savez_compressed(OUT / "ref_linalg.npz", **out)
+    print("ref_linalg.npz", len(out), "arrays")
+
+
+def convert_roots_vectors():
+    """Sage vectors for Poly.roots (tests/polys/data/*/roots.pkl): degree-descending coefficients -> sorted roots."""
+    out = {}
+    for fld in LINALG_FIELDS:
+        d = pickle.load(open(REF / "tests" / "polys" / "data" / fld / "roots.pkl", "rb"))
+        out[f"{fld}/count"] = np.array(len(d["X"]))
+        for i, (x, r, m) in enumerate(zip(d["X"], d["R"], d["M"])):
+            out[f"{fld}/X{i}"] = np.asarray(x, dtype=np.int64)
+            out[f"{fld}/R{i}"] = np.asarray(r, dtype=np.int64)
+            out[f"{fld}/M{i}"] = np.asarray(m, dtype=np.int64)
+    np.savez_compressed(OUT / "ref_roots.npz", **out)
+    print("ref_roots.npz", len(out), "arrays")
+
+
+def live_next_rows():
+    """Live-reference outputs for the §8(f) rows at sizes the Sage vectors do not reach."""
+    out = {}
+    meta = {}
+    rng = np.random.default_rng(2024)
+
+    # ---- Poly.roots: dense and sparse polynomials, roots with multiplicity, the x^q - x extreme, no roots
+    def roots_case(key, GF, poly):
+        out[f"roots/{key}/degrees"] = np.asarray(poly.nonzero_degrees, dtype=np.int64)
+        out[f"roots/{key}/coeffs"] = np.asarray(poly.nonzero_coeffs, dtype=np.int64)
+        out[f"roots/{key}/roots"] = np.asarray(poly.roots(), dtype=np.int64)
+
+    fields = {"gf256": galois.GF(2**8), "gf65536": galois.GF(2**16), "gf7919": galois.GF(7919),
+              "gf998244353_small": None, "gf2": galois.GF(2), "gf31": galois.GF(31)}
+    meta["roots"] = {}
+    for name, GF in fields.items():
+        if GF is None:
+            continue
+        meta["roots"][name] = {"order": int(GF.order), "irreducible_poly": int(GF.irreducible_poly),
+                               "primitive_element": int(GF.primitive_element)}
+        q = GF.order
+        r = GF.Random(min(6, q - 1), seed=int(rng.integers(1 << 30)), low=1)
+        roots_case(f"{name}/from_roots", GF, galois.Poly.Roots(r, multiplicities=[1 + i % 3 for i in range(r.size)]))
+        roots_case(f"{name}/random_dense", GF, galois.Poly.Random(17, seed=int(rng.integers(1 << 30)), field=GF))
+        roots_case(f"{name}/sparse", GF, galois.Poly.Degrees([q + 7, 5, 1], [1, int(GF(q - 1)), 1], field=GF))
+        roots_case(f"{name}/x_q_minus_x", GF, galois.Poly.Degrees([q, 1], [1, int(-GF(1))], field=GF))
+        roots_case(f"{name}/x_pow", GF, galois.Poly.Degrees([9], [1], field=GF))
+        roots_case(f"{name}/constant", GF, galois.Poly([int(GF(1))], field=GF))
+        if q > 2:
+            roots_case(f"{name}/irreducible", GF, galois.irreducible_poly(q, 3))
+    out["roots/names"] = np.array(sorted({k.split("/")[1] + "/" + k.split("/")[2] for k in out if k.startswith("roots/")}))
+
+    # ---- mixed-radix DFT (fft_jit general branch): prime fields with odd / composite sizes, GF(2^m) with n | 2^m - 1
+    meta["fft"] = {}
+    fft_cases = [("gf31", galois.GF(31), [3, 5, 6, 10, 15, 30]),
+                 ("gf998244353", galois.GF(998244353), [7, 17, 119, 14, 7 * 64, 17 * 8 * 7, 1]),
+                 ("gf2147483647", galois.GF(2**31 - 1), [2, 9, 18, 63, 693, 331, 2 * 3 * 7 * 11 * 31]),
+                 ("gf256", galois.GF(2**8), [3, 5, 15, 17, 51, 85, 255]),
+                 ("gf4096", galois.GF(2**12), [9, 63, 65, 455, 4095]),
+                 ("gf65536", galois.GF(2**16), [257, 771])]
+    for name, GF, sizes in fft_cases:
+        meta["fft"][name] = {"order": int(GF.order), "irreducible_poly": int(GF.irreducible_poly),
+                             "primitive_element": int(GF.primitive_element), "sizes": sizes,
+                             "omegas": [int(GF.primitive_root_of_unity(n)) for n in sizes]}
+        for n in sizes:
+            x = GF.Random(n, seed=int(rng.integers(1 << 30)))
+            out[f"fft/{name}/{n}/x"] = np.asarray(x, dtype=np.int64)
+            out[f"fft/{name}/{n}/X"] = np.asarray(np.fft.fft(x), dtype=np.int64)
+            out[f"fft/{name}/{n}/ix"] = np.asarray(np.fft.ifft(x), dtype=np.int64)
+
+    # ---- dense linear algebra at larger shapes, incl. singular / rectangular / ncols-limited cases
+    meta["linalg"] = {}
+    la_fields = {"gf256": galois.GF(2**8), "gf998244353": galois.GF(998244353), "gf2147483647": galois.GF(2**31 - 1),
+                 "gf2": galois.GF(2), "gf2_20": galois.GF(2**20)}
+    for name, GF in la_fields.items():
+        meta["linalg"][name] = {"order": int(GF.order), "irreducible_poly": int(GF.irreducible_poly),
+                                "primitive_element": int(GF.primitive_element)}
+        seed = lambda: int(rng.integers(1 << 30))  # noqa: E731
+        mats = {}
+        mats["sq40"] = GF.Random((40, 40), seed=seed())
+        mats["wide17x45"] = GF.Random((17, 45), seed=seed())
+        mats["tall45x17"] = GF.Random((45, 17), seed=seed())
+        low = GF.Random((30, 6), seed=seed()) @ GF.Random((6, 30), seed=seed())  # rank <= 6
+        mats["rank6_30"] = low
+        z = GF.Random((12, 12), seed=seed())
+        z[:, 0] = 0
+        z[3, :] = 0
+        z[0, 1] = 0
+        mats["zero_col_row"] = z
+        for key, A in mats.items():
+            base = f"linalg/{name}/{key}"
+            out[f"{base}/A"] = np.asarray(A, dtype=np.int64)
+            out[f"{base}/rre"] = np.asarray(A.row_reduce(), dtype=np.int64)
+            nc = max(1, A.shape[1] // 2)
+            out[f"{base}/rre_ncols"] = np.asarray(A.row_reduce(ncols=nc), dtype=np.int64)
+            out[f"{base}/rre_right"] = np.asarray(A.row_reduce(eye="right"), dtype=np.int64)
+            out[f"{base}/rank"] = np.array(int(np.linalg.matrix_rank(A)))
+            P, L, U = A.plu_decompose()
+            out[f"{base}/P"], out[f"{base}/L"], out[f"{base}/U"] = (np.asarray(v, dtype=np.int64) for v in (P, L, U))
+            out[f"{base}/row_space"] = np.asarray(A.row_space(), dtype=np.int64)
+            out[f"{base}/column_space"] = np.asarray(A.column_space(), dtype=np.int64)
+            out[f"{base}/left_null_space"] = np.asarray(A.left_null_space(), dtype=np.int64)
+            out[f"{base}/null_space"] = np.asarray(A.null_space(), dtype=np.int64)
+            try:
+                L2, U2 = A.lu_decompose()
+                out[f"{base}/lu_L"], out[f"{base}/lu_U"] = np.asarray(L2, dtype=np.int64), np.asarray(U2, dtype=np.int64)
+            except (ValueError, IndexError):
+                out[f"{base}/lu_raises"] = np.array(1)
+            if A.shape[0] == A.shape[1]:
+                out[f"{base}/det"] = np.array(int(np.linalg.det(A)))
+                try:
+                    out[f"{base}/inv"] = np.asarray(np.linalg.inv(A), dtype=np.int64)
+                    b1, b2 = GF.Random(A.shape[0], seed=seed()), GF.Random((A.shape[0], 3), seed=seed())
+                    out[f"{base}/b1"], out[f"{base}/b2"] = np.asarray(b1, dtype=np.int64), np.asarray(b2, dtype=np.int64)
+                    out[f"{base}/x1"] = np.asarray(np.linalg.solve(A, b1), dtype=np.int64)
+                    out[f"{base}/x2"] = np.asarray(np.linalg.solve(A, b2), dtype=np.int64)
+                except np.linalg.LinAlgError as e:
+                    out[f"{base}/inv_raises"] = np.array(str(e))
+        meta["linalg"][name]["cases"] = list(mats)
+    np.savez_compressed(OUT / "live_next.npz", **out)
+    json.dump(meta, open(OUT / "live_next_meta.json", "w"), indent=1)
+    print("live_next.npz", len(out), "arrays")
+
+
 def main():
-    which = sys.argv[1:] or ["fields", "rs_ref", "elementwise", "gf128", "ntt", "linalg", "rs", "bch_ref", "bch"]
+    which = sys.argv[1:] or ["fields", "rs_ref", "elementwise", "gf128", "ntt", "linalg", "rs", "bch_ref", "bch",
+                             "linalg_ref", "roots_ref", "next"]
     if "fields" in which:
         convert_field_vectors()
     if "rs_ref" in which:
@@ -501,6 +644,12 @@ def main():
         convert_bch_vectors()
     if "bch" in which:
         live_bch()
+    if "linalg_ref" in which:
+        convert_linalg_vectors()
+    if "roots_ref" in which:
+        convert_roots_vectors()
+    if "next" in which:
+        live_next_rows()
 
 
 if __name__ == "__main__":
