@@ -63,6 +63,19 @@ def _as_u64(v: int) -> ctypes.c_uint64:
     return ctypes.c_uint64(v & 0xFFFFFFFFFFFFFFFF)
 
 
+# np functions answered by galois_b200._linalg (LinalgFunctionMixin._OVERRIDDEN_FUNCTIONS, _domains/_linalg.py:562-575)
+_LINALG_FUNCTIONS = {
+    np.dot: "dot",
+    np.vdot: "vdot",
+    np.inner: "inner",
+    np.outer: "outer",
+    np.linalg.det: "det",
+    np.linalg.matrix_rank: "matrix_rank",
+    np.linalg.solve: "solve",
+    np.linalg.inv: "inv",
+}
+
+
 class FieldArray(np.ndarray, metaclass=FieldMeta):
     """An array over GF(p^m).  Construct concrete classes with :func:`galois_b200.GF`."""
 
@@ -537,7 +550,49 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
             from ._ntt import _fft_dispatch
 
             return _fft_dispatch(field, func is np.fft.ifft, *args, **kwargs)
+        name = _LINALG_FUNCTIONS.get(func)
+        if name is not None:
+            from . import _linalg
+
+            return getattr(_linalg, name)(field, *args, **kwargs)
         return super().__array_function__(func, types, args, kwargs)
+
+    # ------------------------------------------------------------------------------ linear algebra methods
+    def row_reduce(self, ncols=None, eye="left"):
+        """Reduced row echelon form (FieldArray.row_reduce, _fields/_array.py:1412-1469)."""
+        from . import _linalg
+
+        return _linalg.row_reduce(self, ncols=ncols, eye=eye)
+
+    def lu_decompose(self):
+        from . import _linalg
+
+        return _linalg.lu_decompose(self)
+
+    def plu_decompose(self):
+        from . import _linalg
+
+        return _linalg.plu_decompose(self)
+
+    def row_space(self):
+        from . import _linalg
+
+        return _linalg.row_space(self)
+
+    def column_space(self):
+        from . import _linalg
+
+        return _linalg.column_space(self)
+
+    def left_null_space(self):
+        from . import _linalg
+
+        return _linalg.left_null_space(self)
+
+    def null_space(self):
+        from . import _linalg
+
+        return _linalg.null_space(self)
 
     # ------------------------------------------------------------------------------ misc
     def to_device(self):

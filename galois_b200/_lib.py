@@ -58,8 +58,16 @@ SIGNATURES = {
     "gfb_convolve_host": (_int, [_vp, _int, _vp, _sz, _vp, _sz, _vp]),
     "gfb_poly_evaluate": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gfb_poly_evaluate_host": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _sz]),
+    "gfb_poly_roots_workspace_bytes": (_sz, [_vp, _sz]),
+    "gfb_poly_roots": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "gfb_poly_roots_host": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gfb_matmul": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int, _vp]),
     "gfb_matmul_host": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _int]),
+    "gfb_row_reduce_workspace_bytes": (_sz, [_vp, _sz, _sz]),
+    "gfb_row_reduce": (_int, [_vp, _int, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "gfb_row_reduce_host": (_int, [_vp, _int, _vp, _vp, _sz, _sz, _sz, C.POINTER(_i64), _vp]),
+    "gfb_plu_decompose": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _sz, _int, _vp, _vp, _vp]),
+    "gfb_plu_decompose_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _sz, _int, C.POINTER(_i64), C.POINTER(_int)]),
     "gfb_rs_create": (_int, [C.POINTER(_vp), _vp, _int, _int, _int, _u64]),
     "gfb_bch_create": (_int, [C.POINTER(_vp), _vp, _int, _int, _int, _int, _u64, _vp]),
     "gfb_rs_destroy": (None, [_vp]),

@@ -107,3 +107,246 @@ def poly_evaluate(coeffs, x):
         _lib.check(st, "gfb_poly_evaluate_host")
     res = field._from_dev_layout(out, shape, dtype)
     return res if res.ndim else field(int(res.item()), dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Gaussian elimination: row_reduce / lu / plu and what the reference builds from them
+# ------------------------------------------------------------------------------------------------
+def _no_wide(field, what):
+    if field._wide:
+        raise NotImplementedError(f"{what} is not implemented over {field.name} (elements wider than 64 bits).")
+
+
+def _row_reduce_raw(field, A, ncols=None, want_det=False):
+    """gfb_row_reduce_host on a 2-D field array -> (A_rre, n_pivots[, det]); row_reduce_jit.__call__ (_linalg.py:321-353)."""
+    import ctypes
+
+    if not isinstance(A, field):
+        raise TypeError(f"Argument 'A' must be a {field.name} array, not {type(A)}.")
+    if not A.ndim == 2:
+        raise ValueError(f"Only 2-D matrices can be converted to reduced row echelon form, not {A.ndim}-D.")
+    _no_wide(field, "row_reduce")
+    rows, cols = A.shape
+    ncols = cols if ncols is None else int(ncols)
+    if not 0 <= ncols <= cols:
+        raise ValueError(f"Argument 'ncols' must be in [0, {cols}], not {ncols}.")
+    dtype = A.dtype
+    src = np.ascontiguousarray(field._prep(A, dtype))
+    out = _pinned.empty((rows, cols), dtype)
+    n_piv = ctypes.c_int64(0)
+    det = np.zeros(1, dtype=dtype)
+    st = _lib.lib().gfb_row_reduce_host(field._handle(), field._elem_bytes(dtype), src.ctypes.data, out.ctypes.data, rows,
+                                        cols, ncols, ctypes.byref(n_piv), det.ctypes.data if want_det else None)
+    _lib.check(st, "gfb_row_reduce_host")
+    R = np.array(out, dtype=dtype).view(field)
+    if want_det:
+        return R, int(n_piv.value), det
+    return R, int(n_piv.value)
+
+
+def row_reduce(A, ncols=None, eye="left"):
+    """FieldArray.row_reduce (_fields/_array.py:1412-1469)."""
+    if eye not in ("left", "right"):
+        raise ValueError(f"Argument 'eye' must be in ['left', 'right'], not {eye!r}.")
+    field = type(A)
+    if eye == "left":
+        return _row_reduce_raw(field, A, ncols)[0]
+    R = _row_reduce_raw(field, A[::-1, ::-1] if A.ndim == 2 else A, ncols)[0]
+    return R[::-1, ::-1]
+
+
+def _plu_raw(field, A, pivoting: bool):
+    import ctypes
+
+    if not isinstance(A, field):
+        raise TypeError(f"Argument 'A' must be a {field.name} array, not {type(A)}.")
+    if not A.ndim == 2:
+        raise ValueError(f"Argument 'A' must be a 2-D matrix, not have shape {A.shape}.")
+    _no_wide(field, "LU decomposition")
+    m, n = A.shape
+    if m == 0 or n == 0:
+        raise ValueError(f"Argument 'A' must be a non-empty matrix, not have shape {A.shape}.")
+    if not pivoting and m - 1 > n:
+        # lu_decompose_jit walks the diagonal for range(m - 1) (_linalg.py:371-372): Ai[i, i] leaves the matrix
+        raise IndexError(f"index {n} is out of bounds for axis 1 with size {n}")
+    dtype = A.dtype
+    src = np.ascontiguousarray(field._prep(A, dtype))
+    U = _pinned.empty((m, n), dtype)
+    L = _pinned.empty((m, m), dtype)
+    perm = np.zeros(m, dtype=np.int64)
+    n_swaps = ctypes.c_int64(0)
+    failed = ctypes.c_int(0)
+    st = _lib.lib().gfb_plu_decompose_host(field._handle(), field._elem_bytes(dtype), src.ctypes.data, U.ctypes.data,
+                                           L.ctypes.data, perm.ctypes.data, m, n, 1 if pivoting else 0,
+                                           ctypes.byref(n_swaps), ctypes.byref(failed))
+    _lib.check(st, "gfb_plu_decompose_host")
+    if failed.value:
+        raise ValueError("The LU decomposition of 'A' does not exist. Use the PLU decomposition instead.")
+    return (np.array(L, dtype=dtype).view(field), np.array(U, dtype=dtype).view(field), perm, int(n_swaps.value))
+
+
+def lu_decompose(A):
+    """FieldArray.lu_decompose (_fields/_array.py:1471-1502) -> (L, U)."""
+    L, U, _, _ = _plu_raw(type(A), A, pivoting=False)
+    return L, U
+
+
+def plu_decompose(A):
+    """FieldArray.plu_decompose (_fields/_array.py:1504-1539) -> (P, L, U) with A = P L U."""
+    field = type(A)
+    L, U, perm, _ = _plu_raw(field, A, pivoting=True)
+    m = A.shape[0]
+    P_rows = np.zeros((m, m), dtype=A.dtype)
+    P_rows[np.arange(m), perm] = 1  # the reference's row-swapped identity; it returns the transpose (:427-428)
+    return P_rows.T.copy().view(field), L, U
+
+
+def _require_square(A):
+    if not (A.ndim == 2 and A.shape[0] == A.shape[1]):
+        raise np.linalg.LinAlgError(f"Argument 'A' must be square, not {A.shape}.")
+
+
+def matrix_rank(field, A):
+    """matrix_rank_jit (_linalg.py:479-489): non-zero rows of the reduced row echelon form."""
+    R, _ = _row_reduce_raw(field, A)
+    return int(np.sum(~np.all(np.asarray(R) == 0, axis=1)))
+
+
+def inv(field, A):
+    """inv_jit (_linalg.py:492-522): row-reduce [A | I] over the first n columns."""
+    if not isinstance(A, field):
+        raise TypeError(f"Argument 'A' must be a {field.name} array, not {type(A)}.")
+    _require_square(A)
+    n = A.shape[0]
+    AI = np.concatenate((np.asarray(A), np.identity(n, dtype=A.dtype)), axis=-1).view(field)
+    R, _ = _row_reduce_raw(field, AI, ncols=n)
+    rank = int(np.sum(~np.all(np.asarray(R)[:, 0:n] == 0, axis=1)))
+    if not rank == n:
+        raise np.linalg.LinAlgError(
+            f"Argument 'A' is singular and not invertible because it does not have full rank of {n}, but rank of {rank}."
+        )
+    return R[:, -n:] if n else R[:, 0:0]
+
+
+def solve(field, A, b):
+    """solve_jit (_linalg.py:525-546): x = A^-1 b."""
+    if not isinstance(A, field):
+        raise TypeError(f"Argument 'A' must be a {field.name} array, not {type(A)}.")
+    if not isinstance(b, field):
+        raise TypeError(f"Argument 'b' must be a {field.name} array, not {type(b)}.")
+    _require_square(A)
+    if b.ndim not in [1, 2]:
+        raise np.linalg.LinAlgError(f"Argument 'b' must have dimension equal to 'A' or one less, not {b.ndim}.")
+    if not A.shape[-1] == b.shape[0]:
+        raise np.linalg.LinAlgError(
+            f"The last dimension of 'A' must equal the first dimension of 'b', not {A.shape} and {b.shape}."
+        )
+    A_inv = inv(field, A)
+    return matmul(field, np.ascontiguousarray(A_inv).view(field), b)
+
+
+def det(field, A):
+    """
+    det_jit (_linalg.py:446-471).  The reference takes closed forms for n = 2, 3 and (-1)^swaps det(L) det(U) otherwise;
+    the determinant is one field element whichever way it is computed — here it is the signed product of the pivots
+    of the elimination (0 when the matrix is rank deficient).
+    """
+    if not isinstance(A, field):
+        raise TypeError(f"Argument 'A' must be a {field.name} array, not {type(A)}.")
+    _require_square(A)
+    n = A.shape[0]
+    if n == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")  # plu_decompose_jit's L[-1, -1] (:423)
+    _, p, d = _row_reduce_raw(field, A, want_det=True)
+    return field(int(d[0]) if p == n else 0, dtype=A.dtype)
+
+
+def row_space(A):
+    """FieldArray.row_space (_fields/_array.py:1541-1590)."""
+    field = type(A)
+    if not A.ndim == 2:
+        raise ValueError(f"Only 2-D matrices have a row space, not {A.ndim}-D.")
+    R = row_reduce(A)
+    rank = int(np.sum(~np.all(np.asarray(R) == 0, axis=1)))
+    return R[0:rank, :].view(field)
+
+
+def column_space(A):
+    """FieldArray.column_space (_fields/_array.py:1592-1637)."""
+    if not A.ndim == 2:
+        raise ValueError(f"Only 2-D matrices have a column space, not {A.ndim}-D.")
+    return row_space(A.T)
+
+
+def left_null_space(A):
+    """FieldArray.left_null_space (_fields/_array.py:1639-1703): the rows of [A | I] that reduce to zero on the left."""
+    field = type(A)
+    if not A.ndim == 2:
+        raise ValueError(f"Only 2-D matrices have a left null space, not {A.ndim}-D.")
+    m, n = A.shape
+    AI = np.concatenate((np.asarray(A), np.identity(m, dtype=A.dtype)), axis=-1).view(field)
+    R, p = _row_reduce_raw(field, AI, ncols=n)
+    LN = np.ascontiguousarray(np.asarray(R)[p:, n:]).view(field)
+    if LN.shape[0] == 0:
+        return LN
+    return row_reduce(LN)
+
+
+def null_space(A):
+    """FieldArray.null_space (_fields/_array.py:1705-1755)."""
+    if not A.ndim == 2:
+        raise ValueError(f"Only 2-D matrices have a null space, not {A.ndim}-D.")
+    return left_null_space(A.T)
+
+
+# ------------------------------------------------------------------------------------------------
+# np.dot / np.vdot / np.inner / np.outer (dot_jit, vdot_jit, inner_jit, outer_jit: _domains/_linalg.py:81-188)
+# ------------------------------------------------------------------------------------------------
+def _check_pair(field, a, b):
+    if not isinstance(a, field):
+        raise TypeError(f"Argument 'a' must be a {field.name} array, not {type(a)}.")
+    if not isinstance(b, field):
+        raise TypeError(f"Argument 'b' must be a {field.name} array, not {type(b)}.")
+
+
+def dot(field, a, b, out=None):
+    _check_pair(field, a, b)
+    if out is not None:
+        raise NotImplementedError("The 'out' argument is not supported by the CUDA backend's dot().")
+    if a.ndim == 0 or b.ndim == 0:
+        return a * b
+    if a.ndim == 1 and b.ndim == 1:
+        return np.sum(a * b)
+    if a.ndim == 2 and b.ndim == 2:
+        return matmul(field, a, b)
+    if a.ndim >= 2 and b.ndim == 1:
+        return np.sum(a * b, axis=-1)
+    raise NotImplementedError(
+        "Currently 'dot' is only supported up to 2-D matrices. "
+        "Please open a GitHub issue at https://github.com/mhostetter/galois/issues."
+    )
+
+
+def vdot(field, a, b):
+    _check_pair(field, a, b)
+    a = a.flatten()
+    b = b.flatten().reshape(a.shape)  # mimics NumPy's error scenarios, as the reference does
+    return np.sum(a * b)
+
+
+def inner(field, a, b):
+    _check_pair(field, a, b)
+    if a.ndim == 0 or b.ndim == 0:
+        return a * b
+    if not a.shape[-1] == b.shape[-1]:
+        raise ValueError(
+            f"Operation 'inner' requires 'a' and 'b' to have the same last dimension, not {a.shape} and {b.shape}."
+        )
+    return np.sum(a * b, axis=-1)
+
+
+def outer(field, a, b, out=None):
+    _check_pair(field, a, b)
+    if out is not None:
+        raise NotImplementedError("The 'out' argument is not supported by the CUDA backend's outer().")
+    return np.multiply.outer(a.ravel(), b.ravel())

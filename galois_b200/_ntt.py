@@ -32,9 +32,13 @@ def _plan(field, n: int, inverse: bool, scaled: bool):
         if plan is None:
             p = field.characteristic
             omega = int(field.primitive_root_of_unity(n)) if n > 1 else 1
-            if inverse:
-                omega = pow(omega, -1, p)  # omega ** -1, _function.py:194-195
-            scale = pow(n % p, -1, p) if scaled else 1  # y /= field(n % p), _function.py:209-210
+            if inverse:  # omega ** -1 (_function.py:194-195); omega has order n, so omega^-1 = omega^(n-1)
+                if field._is_prime_field:
+                    omega = pow(omega, -1, p)
+                else:
+                    omega = _nt.powmod2(omega, n - 1, int(field.irreducible_poly))
+            # y /= field(n % p) (_function.py:209-210); in characteristic 2 every admissible n is odd: n % 2 = 1
+            scale = (pow(n % p, -1, p) if p > 2 else 1) if scaled else 1
             out = ctypes.c_void_p()
             st = lib.gfb_ntt_plan_create(ctypes.byref(out), h, n, ctypes.c_uint64(omega), ctypes.c_uint64(scale))
             _lib.check(st, f"gfb_ntt_plan_create(n={n})")
@@ -46,12 +50,8 @@ def _plan(field, n: int, inverse: bool, scaled: bool):
 def _check_size(field, n: int):
     if n < 1:
         raise ValueError(f"Argument 'n' must be at least 1, not {n}.")
-    if n & (n - 1):
-        raise NotImplementedError(
-            f"Transform size {n} is not a power of two: mixed-radix sizes are outside the CUDA hot path (SURVEY.md §8f.3)."
-        )
-    if not field._is_prime_field:
-        raise NotImplementedError("The CUDA FFT is implemented over prime fields only (SURVEY.md §8f.3).")
+    if field._wide:
+        raise NotImplementedError(f"The CUDA FFT is not implemented over {field.name} (degree above 63).")
     if (field.order - 1) % n != 0:
         raise ValueError(f"There are no primitive {n}-th roots of unity in {field.name}.")
 

@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "gfb_common.cuh"
+#include "gfb_dispatch.cuh"
 #include "gfb_host.cuh"
 
 struct gfb_ntt_plan {
@@ -41,6 +42,12 @@ struct gfb_ntt_plan {
     uint2* d_zt;           // pass 2: [k1*32 + t] = (zeta2^(t k1), shoup), zeta2 = omega^n1 (1024th root), k1 < 32
     uint2* d_zt1;          // pass 1: [k1*32 + t] = (zeta1^(t k1), shoup), zeta1 = omega^1024 (n1-th root), k1 < n1/32
     uint32_t rho[16], rho_sh[16];  // rho^e, rho = zeta^32 (primitive 32nd root), with Shoup companions
+    // mixed-radix path (any N | order - 1, prime or binary field): the reference's general stage, one launch per factor
+    bool mixed;
+    int n_factors;
+    uint32_t factors[32];  // prime factors of N with multiplicity, ascending (fft_jit._prime_factors)
+    uint64_t omega64, scale64;
+    void* d_pow_mixed;     // omega^e, e < N, in the field's compute element type
 };
 
 namespace gfb {
@@ -113,6 +120,75 @@ template <typename T>
 __global__ void k_scale_copy(PrimeBarrett f, const T* in, T* out, size_t count, uint32_t scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = (T)f.mul((uint32_t)in[i], scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixed-radix path: the general radix-r stage of fft_jit.implementation (_function.py:354-376), one output per thread
+//   in_view[k, qi, b] = in[(k*q + qi)*m + b],  out_view[qi, fo, b] = out[(qi*r + fo)*m + b],
+//   out = sum_k in_view[k] * tw^k (Horner),  tw = omega^(q*(fo*m + b))   — the reference's running twiddle
+// Works over any field functor (prime or binary), any N dividing order - 1.
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+__global__ void k_build_pow_any(F f, typename F::elem omega, typename F::elem* out, size_t count, size_t fs) {
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = i == 0 ? f.one() : f.pow_u64(omega, i);
+}
+
+// ok[0] = 1 iff omega^n == 1 and omega^(n/q) != 1 for every prime factor q of n (omega has order exactly n)
+template <typename F>
+__global__ void k_check_root(F f, typename F::elem omega, unsigned long long n, const uint32_t* __restrict__ factors,
+                             int nf, int* ok) {
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool good = !f.is_zero(omega) && f.pow_u64(omega, n) == f.one();
+    for (int i = 0; i < nf && good; ++i) {
+        if (i && factors[i] == factors[i - 1]) continue;
+        if (f.pow_u64(omega, n / factors[i]) == f.one()) good = false;
+    }
+    *ok = good ? 1 : 0;
+}
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(256)
+k_mixed_stage(F f, const T* __restrict__ in, T* __restrict__ out, const typename F::elem* __restrict__ pow, size_t n,
+              size_t m, size_t r, size_t batch, typename F::elem scale, int apply_scale, size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    const size_t total = n * batch;
+    const size_t q = n / (m * r);
+    const size_t rm = r * m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = idx / n;
+        const size_t o = idx - row * n;
+        const size_t qi = o / rm;
+        const size_t rem = o - qi * rm;  // fo*m + b
+        const size_t b = rem % m;
+        const T* src = in + row * n + qi * m + b;
+        const E tw = pow[q * rem];       // q * rem < q*r*m = n
+        const size_t kstride = q * m;
+        E acc = to_elem<E, T>(src[(r - 1) * kstride]);
+        for (size_t k = r - 1; k-- > 0;) acc = f.add(f.mul(acc, tw), to_elem<E, T>(src[k * kstride]));
+        if (apply_scale) acc = f.mul(acc, scale);
+        out[idx] = to_store<T, E>(acc);
+    }
+}
+
+template <typename T, typename F>
+__global__ void k_mixed_scale(F f, const T* __restrict__ in, T* __restrict__ out, size_t count, typename F::elem scale,
+                              size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = to_store<T, E>(f.mul(to_elem<E, T>(in[i]), scale));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -637,6 +713,89 @@ static gfb_status run_generic_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch
     return GFB_OK;
 }
 
+static size_t mixed_rows_per_chunk(const gfb_ntt_plan* pl, int eb) {
+    const size_t rows = kGenericWsBytes / (pl->n * (size_t)eb);
+    return rows ? rows : 1;
+}
+
+template <typename T, typename F>
+static gfb_status run_mixed_t(gfb_ntt_plan* pl, F f, const T* x, T* y, size_t batch, void* workspace, cudaStream_t st) {
+    using E = typename F::elem;
+    const size_t n = pl->n;
+    const size_t fs = field_smem_bytes(f);
+    const E scale = (E)pl->scale64;
+    const E* pow = (const E*)pl->d_pow_mixed;
+    const int S = pl->n_factors;
+    if (S == 0) {  // N = 1
+        k_mixed_scale<T, F><<<(unsigned)((batch + 255) / 256), 256, fs, st>>>(f, x, y, batch, scale, fs);
+        GFB_CUDA_TRY(cudaGetLastError());
+        return GFB_OK;
+    }
+    const size_t rows_per_chunk = mixed_rows_per_chunk(pl, (int)sizeof(T));
+    T* A = (T*)workspace;
+    T* B = A ? A + rows_per_chunk * n : nullptr;
+    for (size_t off = 0; off < batch; off += rows_per_chunk) {
+        const size_t cnt = batch - off < rows_per_chunk ? batch - off : rows_per_chunk;
+        size_t blocks = (n * cnt + 255) / 256;
+        const size_t cap = (size_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        const T* src = x + off * n;
+        size_t m = 1;
+        for (int s = 0; s < S; ++s) {
+            const size_t r = pl->factors[S - 1 - s];  // radices are consumed from the end (_function.py:312-314)
+            const bool last = s == S - 1;
+            T* dst = last ? y + off * n : ((s & 1) ? B : A);
+            k_mixed_stage<T, F><<<(unsigned)blocks, 256, fs, st>>>(f, src, dst, pow, n, m, r, cnt, scale,
+                                                                     last && pl->scale64 != 1ull, fs);
+            src = dst;
+            m *= r;
+        }
+    }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+static gfb_status run_mixed(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t batch, void* workspace,
+                            cudaStream_t st) {
+    auto go = [&](auto functor) -> gfb_status {
+        if (eb == 4) return run_mixed_t<uint32_t>(pl, functor, (const uint32_t*)x, (uint32_t*)y, batch, workspace, st);
+        return run_mixed_t<unsigned long long>(pl, functor, (const unsigned long long*)x, (unsigned long long*)y, batch,
+                                               workspace, st);
+    };
+    const gfb_field* f = pl->field;
+    switch (f->impl) {
+        case IMPL_PRIME_M31: return go(f->prime_m31());
+        case IMPL_PRIME_BARRETT: return go(f->prime_barrett());
+        case IMPL_BIN_LUT: return go(f->bin_lut());
+        case IMPL_BIN_CALC: return go(f->bin_calc());
+        default: break;
+    }
+    return GFB_ERR_UNSUPPORTED;
+}
+
+// tables + primitivity check of the mixed-radix plan
+template <typename F>
+static cudaError_t mixed_setup(gfb_ntt_plan* pl, F f, int* ok_out) {
+    using E = typename F::elem;
+    const size_t n = pl->n;
+    const size_t fs = field_smem_bytes(f);
+    uint32_t* d_factors = nullptr;
+    int* d_ok = nullptr;
+    cudaError_t e = cudaMalloc((void**)&pl->d_pow_mixed, n * sizeof(E));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_factors, sizeof(pl->factors));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_ok, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d_factors, pl->factors, sizeof(pl->factors), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_check_root<F><<<1, 32, fs>>>(f, (E)pl->omega64, (unsigned long long)n, d_factors, pl->n_factors, d_ok);
+        k_build_pow_any<F><<<(unsigned)((n + 255) / 256), 256, fs>>>(f, (E)pl->omega64, (E*)pl->d_pow_mixed, n, fs);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(ok_out, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_factors);
+    cudaFree(d_ok);
+    return e;
+}
+
 static uint32_t host_powmod(uint32_t b, unsigned long long e, uint32_t p) {
     unsigned long long r = 1 % p, x = b % p;
     while (e) {
@@ -655,9 +814,46 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
     using namespace gfb;
     if (!out) return GFB_ERR_BAD_ARG;
     *out = nullptr;
-    if (!f || f->kind != GFB_PRIME) return GFB_ERR_BAD_ARG;
-    if (n == 0 || (n & (n - 1)) != 0) return GFB_ERR_UNSUPPORTED;  // mixed radix: SURVEY.md §8f.3
+    if (!f || n == 0) return GFB_ERR_BAD_ARG;
     if (n > ((size_t)1 << 24)) return GFB_ERR_UNSUPPORTED;
+    if (f->kind != GFB_PRIME || (n & (n - 1)) != 0) {
+        // any N | order - 1 over a prime or binary field: the reference's mixed-radix stages
+        if (f->impl == IMPL_BIN_128 || f->order_lo == 0) return GFB_ERR_UNSUPPORTED;
+        if ((f->order_lo - 1) % n != 0) return GFB_ERR_BAD_ARG;
+        if (omega >= f->order_lo || scale >= f->order_lo || scale == 0) return GFB_ERR_BAD_ARG;
+        gfb_ntt_plan* pl = (gfb_ntt_plan*)calloc(1, sizeof(gfb_ntt_plan));
+        pl->field = f;
+        pl->n = n;
+        pl->mixed = true;
+        pl->omega64 = omega;
+        pl->scale64 = scale;
+        size_t rest = n;
+        for (size_t d = 2; d * d <= rest; ++d)
+            while (rest % d == 0) {
+                pl->factors[pl->n_factors++] = (uint32_t)d;
+                rest /= d;
+            }
+        if (rest > 1) pl->factors[pl->n_factors++] = (uint32_t)rest;
+        int ok = 0;
+        cudaError_t e = cudaSuccess;
+        switch (f->impl) {
+            case IMPL_PRIME_M31: e = mixed_setup(pl, f->prime_m31(), &ok); break;
+            case IMPL_PRIME_BARRETT: e = mixed_setup(pl, f->prime_barrett(), &ok); break;
+            case IMPL_BIN_LUT: e = mixed_setup(pl, f->bin_lut(), &ok); break;
+            default: e = mixed_setup(pl, f->bin_calc(), &ok); break;
+        }
+        if (e != cudaSuccess) {
+            set_last_error("gfb_ntt_plan_create (mixed radix)", e);
+            gfb_ntt_plan_destroy(pl);
+            return GFB_ERR_CUDA;
+        }
+        if (!ok) {  // omega is not a primitive n-th root of unity
+            gfb_ntt_plan_destroy(pl);
+            return GFB_ERR_BAD_ARG;
+        }
+        *out = pl;
+        return GFB_OK;
+    }
     const uint32_t p = f->p;
     if (omega >= p || scale >= p || scale == 0) return GFB_ERR_BAD_ARG;
     if (((unsigned long long)p - 1ull) % n != 0) return GFB_ERR_BAD_ARG;
@@ -731,13 +927,18 @@ void gfb_ntt_plan_destroy(gfb_ntt_plan* pl) {
     if (pl->d_tw4) cudaFree(pl->d_tw4);
     if (pl->d_zt) cudaFree(pl->d_zt);
     if (pl->d_zt1) cudaFree(pl->d_zt1);
+    if (pl->d_pow_mixed) cudaFree(pl->d_pow_mixed);
     free(pl);
 }
 
 size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t batch) {
     using namespace gfb;
-    (void)elem_bytes;
     if (!pl || batch == 0) return 0;
+    if (pl->mixed) {
+        if (pl->n_factors <= 1) return 0;  // a single stage goes straight from x to y
+        const size_t cap = mixed_rows_per_chunk(pl, elem_bytes);
+        return 2 * (batch < cap ? batch : cap) * pl->n * (size_t)elem_bytes;
+    }
     if (pl->fast) {
         if (pl->log_n <= 10) return 0;  // single kernel
         const size_t chunk = fast_chunk(pl);
@@ -758,6 +959,10 @@ gfb_status gfb_ntt_exec(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t
     if (eb != 4 && eb != 8) return GFB_ERR_BAD_ARG;
     if (gfb_ntt_workspace_bytes(pl, eb, batch) != 0 && !workspace) return GFB_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->mixed) {
+        if (pl->n_factors == 1 && x == y) return GFB_ERR_BAD_ARG;  // one out-of-place stage
+        return run_mixed(pl, eb, x, y, batch, workspace, st);
+    }
     if (pl->fast) {
         uint32_t* ws = (uint32_t*)workspace;
         if (eb == 4)

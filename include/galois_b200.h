@@ -132,19 +132,24 @@ gfb_status gfb_power_scalar_host(gfb_field* f, int elem_bytes, const void* a, in
 
 /* ----------------------------------------------------------------- NTT / INTT */
 /* Replaces fft_jit / ifft_jit (_domains/_function.py:170-392) behind galois.ntt/intt
- * (_ntt.py:16-278) for radix-2 sizes over prime fields, and ADDS the batch dimension
+ * (_ntt.py:16-278) and np.fft.fft/ifft on field arrays, and ADDS the batch dimension
  * the reference lacks (it is 1-D only, _function.py:180-181).
- *   X[b][k] = scale * sum_j x[b][j] * omega^(j*k)  (mod p), natural order in and out.
- * `n` must be a power of two, 1 <= n <= 2^24, n | p-1; `omega` a primitive n-th root of
- * unity chosen by the caller exactly as the reference does (FieldArray.primitive_root_of_unity,
- * _fields/_array.py:1127-1187; its inverse for INTT, _function.py:194-195); `scale` is 1 or
+ *   X[b][k] = scale * sum_j x[b][j] * omega^(j*k)  in the field, natural order in and out.
+ * `n` is any size with 1 <= n <= 2^24 and n | order-1:
+ *   - powers of two over GF(p) take the radix-2 / four-step kernels (_function.py:337-352),
+ *   - every other size, and GF(2^m) with m <= 63, take the reference's general mixed-radix
+ *     stages (_function.py:354-376; prime factors of n with multiplicity, consumed from the end).
+ * `omega` is a primitive n-th root of unity chosen by the caller exactly as the reference does
+ * (FieldArray.primitive_root_of_unity, _fields/_array.py:1127-1187; its inverse for the inverse
+ * transform, _function.py:194-195) — GFB_ERR_BAD_ARG if it does not have order n; `scale` is 1 or
  * (n mod p)^-1 (_function.py:209-210). */
 gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint64_t omega,
                                uint64_t scale);
 void gfb_ntt_plan_destroy(gfb_ntt_plan* plan);
 /* Bytes of device workspace gfb_ntt_exec needs for `batch` transforms (0 if none). */
 size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* plan, int elem_bytes, size_t batch);
-/* x, y: [batch][n] contiguous device arrays of elem_bytes ∈ {4, 8}; y may alias x. */
+/* x, y: [batch][n] contiguous device arrays of elem_bytes ∈ {4, 8}; y may alias x, except for a prime
+ * non-power-of-two n (a single out-of-place stage: GFB_ERR_BAD_ARG). */
 gfb_status gfb_ntt_exec(gfb_ntt_plan* plan, int elem_bytes, const void* x, void* y, size_t batch,
                         void* workspace, void* stream);
 gfb_status gfb_ntt_exec_host(gfb_ntt_plan* plan, int elem_bytes, const void* x, void* y,
@@ -164,12 +169,53 @@ gfb_status gfb_poly_evaluate(gfb_field* f, int elem_bytes, const void* coeffs, s
                              void* y, size_t n, void* stream);
 gfb_status gfb_poly_evaluate_host(gfb_field* f, int elem_bytes, const void* coeffs, size_t nc, const void* x,
                                   void* y, size_t n);
+/* All roots of f(x) = sum_j coeffs[j] x^degrees[j] in the field, in increasing order — roots_jit
+ * (_polys/_dense.py:443-513: Chien search + argsort) behind Poly.roots (_polys/_poly.py:711-790).
+ * `degrees` (HOST array, strictly descending, >= 0) and `coeffs` (non-zero coefficients, device / host per variant)
+ * are Poly.nonzero_degrees / Poly.nonzero_coeffs.  At most max_roots roots are written; *n_roots receives how many
+ * the polynomial has (<= its degree for a non-zero polynomial).  Fields with more than 2^33 elements return
+ * GFB_ERR_UNSUPPORTED (the search is exhaustive, as the reference's is).  The device variant needs
+ * gfb_poly_roots_workspace_bytes() of device scratch and writes the count to device memory. */
+size_t gfb_poly_roots_workspace_bytes(const gfb_field* f, size_t n_terms);
+gfb_status gfb_poly_roots(gfb_field* f, int elem_bytes, const int64_t* degrees, const void* coeffs,
+                          size_t n_terms, void* roots, size_t max_roots, unsigned long long* n_roots,
+                          void* workspace, void* stream);
+gfb_status gfb_poly_roots_host(gfb_field* f, int elem_bytes, const int64_t* degrees, const void* coeffs,
+                               size_t n_terms, void* roots, size_t max_roots, size_t* n_roots);
 /* C[batch][M][N] = A[batch][M][K] · B[batch or 1][K][N] over the field.  matmul_jit
  * (_domains/_linalg.py:180-308).  b_batched = 0 broadcasts one B to every batch. */
 gfb_status gfb_matmul(gfb_field* f, int elem_bytes, const void* A, const void* B, void* C,
                       size_t batch, size_t M, size_t K, size_t N, int b_batched, void* stream);
 gfb_status gfb_matmul_host(gfb_field* f, int elem_bytes, const void* A, const void* B, void* C,
                            size_t batch, size_t M, size_t K, size_t N, int b_batched);
+
+/* ------------------------------------------------- Gaussian elimination ---- */
+/* Reduced row echelon form of the row-major rows x cols matrix A, in place, with pivots searched in the first
+ * `ncols` columns only — row_reduce_jit.__call__ (_domains/_linalg.py:321-353), including its pivoting rule (first
+ * non-zero entry at or below the pivot row), which the [A | I] callers depend on: inv_jit (:492-522), solve_jit
+ * (:525-546), matrix_rank_jit (:479-489), FieldArray.row_space / column_space / left_null_space / null_space
+ * (_fields/_array.py:1541-1755).  SURVEY.md §8f rank 4.
+ *   info (device, 2 x int64): [0] = number of pivots p, [1] = number of row exchanges.
+ *   det  (device, elem_bytes, may be NULL): (-1)^exchanges x product of the pivots — det(A) when A is square,
+ *        ncols == cols and p == rows (the value det_jit :446-471 computes through PLU; 0 otherwise is the caller's job).
+ * The device variant needs gfb_row_reduce_workspace_bytes() of scratch.  Fields wider than 64 bits: UNSUPPORTED. */
+size_t gfb_row_reduce_workspace_bytes(const gfb_field* f, size_t rows, size_t cols);
+gfb_status gfb_row_reduce(gfb_field* f, int elem_bytes, void* A, size_t rows, size_t cols, size_t ncols,
+                          int64_t* info, void* det, void* workspace, void* stream);
+gfb_status gfb_row_reduce_host(gfb_field* f, int elem_bytes, const void* A, void* A_rre, size_t rows,
+                               size_t cols, size_t ncols, int64_t* n_pivots, void* det);
+/* A = P L U.  pivoting != 0: plu_decompose_jit.__call__ (_domains/_linalg.py:390-428) — rows are exchanged only when
+ * the diagonal entry is zero, with the first non-zero entry below it; pivoting == 0: lu_decompose_jit.__call__
+ * (:356-387), which fails (info[1] = 1; the reference raises ValueError) when an exchange would be needed and requires
+ * rows - 1 <= cols.  A (rows x cols) becomes U in place, L is rows x rows, perm[i] (int64) is the row of A that ended
+ * up as row i (the reference's row-swapped identity has a 1 at [i, perm[i]]; it returns the transpose).
+ *   info (device, 2 x int64): [0] = number of row exchanges, [1] = LU-without-pivoting failed.
+ * Same workspace as gfb_row_reduce. */
+gfb_status gfb_plu_decompose(gfb_field* f, int elem_bytes, void* A, void* L, int64_t* perm, size_t rows,
+                             size_t cols, int pivoting, int64_t* info, void* workspace, void* stream);
+gfb_status gfb_plu_decompose_host(gfb_field* f, int elem_bytes, const void* A, void* U, void* L,
+                                  int64_t* perm, size_t rows, size_t cols, int pivoting,
+                                  int64_t* n_swaps, int* failed);
 
 /* ------------------------------------------------------------ Reed-Solomon ---- */
 /* Replaces ReedSolomon.__init__ (_codes/_reed_solomon.py:111-218) +

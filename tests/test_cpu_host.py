@@ -165,3 +165,79 @@ def test_bch_construction_matches_reference(live_bch):
         gb.BCH(15)
     with pytest.raises(NotImplementedError):
         gb.BCH(13, 4, field=gb.GF(3))
+
+
+def test_poly_holder_and_argument_checks_need_no_gpu():
+    """Poly construction (sparse storage, negative literals, asc/desc order) and the argument errors raised before any
+    kernel is reached (roots_jit.__call__ _polys/_dense.py:448-452, Poly.Degrees _polys/_poly.py:426-520)."""
+    GF = gb.GF(7)
+    p = gb.Poly([1, 0, -5, 0], field=GF)
+    assert p.degree == 3 and p.nonzero_degrees.tolist() == [3, 1] and np.asarray(p.nonzero_coeffs).tolist() == [1, 2]
+    assert np.asarray(p.coeffs).tolist() == [1, 0, 2, 0]
+    assert gb.Poly([0, 2, 0, 1], field=GF, order="asc") == p
+    q = gb.Poly.Degrees([1, 9, 5], [1, 1, -1], field=GF)
+    assert q.nonzero_degrees.tolist() == [9, 5, 1] and np.asarray(q.nonzero_coeffs).tolist() == [1, 6, 1]
+    assert gb.Poly([1, 1]).field is gb.GF(2)  # default field, like galois.Poly
+    G8 = gb.GF(2**8)
+    assert np.asarray(gb.Poly([3, -7], field=G8).nonzero_coeffs).tolist() == [3, 7]  # -c = c in characteristic 2
+    with pytest.raises(ValueError):
+        gb.Poly.Degrees([3, 3], [1, 1], field=GF)
+    with pytest.raises(ValueError):
+        gb.Poly.Degrees([-1], [1], field=GF)
+    with pytest.raises(TypeError):
+        gb.poly_roots([2, 0], GF([1, 1]))
+    with pytest.raises(TypeError):
+        gb.poly_roots(np.array([2, 0]), np.array([1, 1]))
+    with pytest.raises(ValueError):
+        gb.poly_roots(np.array([], dtype=np.int64), GF([]))
+    with pytest.raises(TypeError):
+        p.roots(multiplicity=1)
+    with pytest.raises(NotImplementedError):
+        gb.poly_roots(np.array([1, 0]), gb.GF(2**100)([1, 1]))
+
+
+def test_linalg_argument_checks_need_no_gpu():
+    """Shape / type errors of the elimination family mirror the reference's and are raised before any kernel runs
+    (tests/fields/test_linalg.py:291-299, 321-351, 395-403, 415-423, 435-457, 471-539)."""
+    GF = gb.GF(2**8)
+    v, t = GF.Random(5, seed=1), GF.Random((2, 2, 2), seed=2)
+    for bad in (v, t):
+        with pytest.raises(ValueError):
+            bad.row_reduce()
+        with pytest.raises(ValueError):
+            bad.lu_decompose()
+        with pytest.raises(ValueError):
+            bad.plu_decompose()
+        for method in ("row_space", "column_space", "left_null_space", "null_space"):
+            with pytest.raises(ValueError):
+                getattr(bad, method)()
+    A = GF.Random((2, 3), seed=3)
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.inv(A)
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.det(A)
+    S = GF.Random((3, 3), seed=4)
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.solve(A, GF.Random(3, seed=5))
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.solve(S, GF.Random((3, 2, 2), seed=5))
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.solve(S, GF.Random(4, seed=5))
+    with pytest.raises(TypeError):
+        np.linalg.solve(S, np.asarray(v[:3]))
+    with pytest.raises(ValueError):
+        S.row_reduce(eye="middle")
+    with pytest.raises(TypeError):
+        np.dot(S, np.asarray(S))
+    with pytest.raises(ValueError):
+        np.inner(GF.Random((2, 3), seed=6), GF.Random((2, 4), seed=7))
+
+
+def test_fft_size_checks_need_no_gpu():
+    """Any n dividing order - 1 is a legal transform size now (mixed radix); everything else is a ValueError."""
+    with pytest.raises(ValueError):
+        np.fft.fft(gb.GF(31).Random(7, seed=1))
+    with pytest.raises(ValueError):
+        np.fft.fft(gb.GF(2**8).Random(16, seed=1))
+    with pytest.raises(NotImplementedError):
+        np.fft.fft(gb.GF(2**100).Random(3, seed=1))
