@@ -702,6 +702,199 @@ WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode,
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
+class MatInv:
+    """inverse of a 1024 x 1024 matrix over GF(998244353) by row-reducing [A | I] (inv_jit)."""
+
+    metric, unit, dtype, scaling = "gfp_matinv_1024_per_sec", "inv/s", "uint32", "weak"
+    kernel = "k_eliminate (+ k_rr_pivot per column)"
+    n = 1024
+    bytes_per_unit = 2 * 4 * 1024 * 1024  # compulsory: read A, write A^-1 (the n^3 update traffic is the algorithm's own)
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200 import _linalg
+
+        self.gb, self.torch, self._linalg = gb, torch, _linalg
+        self.GF = gb.GF(P_NTT)
+        n = self.n
+        self.name = f"inverse of a {n}x{n} matrix over GF(998244353) via row_reduce([A | I], ncols={n}), one matrix per GPU per step"
+        g = torch.Generator(device="cuda").manual_seed(11 + rank)
+        a = torch.randint(0, P_NTT, (n, n), dtype=torch.int32, device="cuda", generator=g)
+        ai = torch.cat([a, torch.eye(n, dtype=torch.int32, device="cuda")], dim=1).contiguous()
+        self.a = a
+        self.src = gb.DeviceArray(self.GF, ai.view(torch.uint8).reshape(-1), (n, 2 * n), np.uint32)
+        self.out = gb.DeviceArray.empty(self.GF, (n, 2 * n), np.uint32)
+        self.units_per_step = 1
+        self.launches_per_step = 2 * n + 2
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        _, self.info, _ = self._linalg.row_reduce_device(self.src, ncols=self.n, out=self.out)
+
+    def check(self):
+        # A . A^-1 == I through the matmul kernel, and the left block reduced to the identity with n pivots
+        n, torch = self.n, self.torch
+        assert int(self.info[0].item()) == n, "matrix was singular (seeded input should not be)"
+        R = self.out.tensor.view(torch.int32).view(n, 2 * n)
+        assert torch.equal(R[:, :n], torch.eye(n, dtype=torch.int32, device="cuda"))
+        A = self.gb.DeviceArray(self.GF, self.a.contiguous().view(torch.uint8).reshape(-1), (n, n), np.uint32).cpu()
+        Ainv = R[:, n:].contiguous().cpu().numpy().astype(np.uint32).view(self.GF)
+        assert np.array_equal(np.asarray(A @ Ainv), np.identity(n, dtype=np.uint32)), "A @ A^-1 != I"
+
+    def e2e_setup(self):
+        self.hA = self.GF.Random((self.n, self.n), seed=11)
+        self.h2d = self.n * 2 * self.n * 4
+        self.d2h = self.n * 2 * self.n * 4
+        self.e2e_units = 1
+
+    def e2e_step(self):
+        self.hz = np.linalg.inv(self.hA)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        if not hasattr(self, "cA"):
+            self.cA = np.random.default_rng(11).integers(0, P_NTT, (self.n, self.n), dtype=np.int64)
+        F.matrix_inv(self.cA)
+        return 1
+
+    cpu_sample = "the same 1024x1024 inversion, one thread (row_reduce_jit is a serial NumPy/ufunc loop in the reference)"
+
+
+class PolyRoots:
+    """all roots of a degree-64 polynomial over GF(2^31 - 1) (roots_jit: exhaustive search)."""
+
+    metric, unit, dtype, scaling = "gfp_poly_roots_points_per_sec", "points/s", "uint32", "weak"
+    kernel = "k_roots (count pass + write pass)"
+    degree = 64
+    bytes_per_unit = 0  # no array traffic: 2^31 field elements are generated from the thread index (ALU-bound)
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200 import _linalg
+
+        self.gb, self.torch, self._linalg = gb, torch, _linalg
+        self.GF = gb.GF(2**31 - 1)
+        p = 2**31 - 1
+        self.name = f"roots of a degree-{self.degree} polynomial with 24 planted roots over GF(2^31-1): every field element tested"
+        import oracle
+
+        F = oracle.Field.prime(p)  # test infrastructure builds the planted polynomial (not timed)
+        rng = np.random.default_rng(21 + rank)
+        self.planted = np.unique(rng.integers(0, p, 24))
+        poly = rng.integers(1, p, self.degree + 1 - self.planted.size)
+        for z in self.planted:
+            poly = F.convolve(poly, np.array([1, (p - int(z)) % p]))
+        self.coeffs_host = self.GF(poly.astype(np.int64))
+        nz = np.nonzero(poly)[0]
+        self.degrees = (poly.size - 1 - nz).astype(np.int64)
+        self.coeffs = self.GF(poly[nz]).to_device()
+        self.units_per_step = p
+        self.launches_per_step = 3
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        self.roots, self.count = self._linalg.poly_roots_device(self.degrees, self.coeffs)
+
+    def check(self):
+        n = int(self.count.item())
+        got = self.roots.cpu()[:n]
+        assert set(self.planted.tolist()) <= set(np.asarray(got).tolist()), "planted roots missing"
+        assert np.all(np.diff(np.asarray(got).astype(np.int64)) > 0), "roots are not in increasing order"
+        assert not np.asarray(self.gb.poly_evaluate(self.coeffs_host, got)).any(), "a reported root is not a root"
+
+    def e2e_setup(self):
+        self.poly = self.gb.Poly(self.coeffs_host)
+        self.h2d = 4 * (self.degree + 1)
+        self.d2h = 4 * self.degree
+        self.e2e_units = 2**31 - 1
+
+    def e2e_step(self):
+        self.hz = self.poly.roots()
+
+    def cpu_step(self, threads):
+        import oracle
+
+        F = oracle.Field.prime(2**31 - 1)
+        n = 1 << 20
+        if not hasattr(self, "cx"):
+            self.cc = np.random.default_rng(21).integers(1, 2**31 - 1, self.degree + 1, dtype=np.int64)
+            self.cx = np.arange(1, n + 1, dtype=np.int64)
+        F.poly_evaluate(self.cc, self.cx)
+        return n
+
+    cpu_sample = ("2^20 of the 2^31 - 1 points, one thread, Horner evaluation (degree multiplies + adds per point, the "
+                  "same count as the reference's Chien step lambda_j *= alpha^j)")
+
+
+class FftMixed:
+    """mixed-radix DFT, N = 7 * 17 * 2^13 = 974848 over GF(998244353) (fft_jit general branch)."""
+
+    metric, unit, dtype, scaling = "fft_mixed_974848_per_sec", "FFT/s", "uint32", "weak"
+    kernel = "k_mixed_stage (15 stages: 2 x13, 7, 17)"
+    N = 7 * 17 * 2**13
+    bytes_per_unit = 2 * 4 * 7 * 17 * 2**13
+
+    def __init__(self, rank, world, batch=64):
+        import torch
+
+        import galois_b200 as gb
+
+        self.gb, self.torch = gb, torch
+        self.GF = gb.GF(P_NTT)
+        self.rows = batch
+        self.name = f"mixed-radix DFT N=7*17*2^13 over GF(998244353), batch {batch} per GPU"
+        g = torch.Generator(device="cuda").manual_seed(31 + rank)
+        x = torch.randint(0, P_NTT, (self.rows, self.N), dtype=torch.int32, device="cuda", generator=g)
+        self.x = gb.DeviceArray(self.GF, x.view(torch.uint8).reshape(-1), (self.rows, self.N), np.uint32)
+        self.out = gb.DeviceArray.empty(self.GF, (self.rows, self.N), np.uint32)
+        self.units_per_step = self.rows
+        self.launches_per_step = 15 * ((self.rows * self.N * 4 + (64 << 20) - 1) // (64 << 20))
+        self.h2d = self.d2h = 0
+
+    def step(self):
+        self.gb.ntt_device(self.x, out=self.out)
+
+    def check(self):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        omega = int(self.GF.primitive_root_of_unity(self.N))
+        row = self.x.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        got = self.out.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, F.fft(row, omega)), "GPU mixed-radix DFT differs from the oracle"
+
+    def e2e_setup(self):
+        self.e2e_rows = min(self.rows, 32)
+        self.hx = self.GF.Random((self.e2e_rows, self.N), seed=31)
+        self.h2d = self.d2h = 4 * self.N * self.e2e_rows
+        self.e2e_units = self.e2e_rows
+
+    def e2e_step(self):
+        self.hz = np.fft.fft(self.hx)
+
+    def cpu_step(self, threads):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        rows = max(threads, 8)
+        if not hasattr(self, "cx"):
+            self.cx = np.random.default_rng(31).integers(0, P_NTT, (rows, self.N), dtype=np.int64)
+            self.omega = int(self.GF.primitive_root_of_unity(self.N))
+        F.fft(self.cx, self.omega, threads=threads)
+        return rows
+
+    cpu_sample = "max(threads, 8) transforms (one fft_jit-style mixed-radix transform per row, rows over OpenMP threads)"
+
+
+WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMixed})
+
+
 def cpu_threads() -> int:
     import oracle
 
@@ -735,7 +928,7 @@ def run_reference(args):
 
         work.GF = gb.GF(cls.field_order, **cls.field_kw)  # host-side description of the field only
         work.name = f"{work.GF.name} {cls.op}"
-    if issubclass(cls, Ntt):
+    if issubclass(cls, (Ntt, FftMixed)):
         import galois_b200 as gb
 
         work.GF = gb.GF(P_NTT)  # host-side constants only (omega)
@@ -803,7 +996,7 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     cls = WORKLOADS[args.workload]
     kw = {}
-    if args.batch is not None and issubclass(cls, Ntt):
+    if args.batch is not None and issubclass(cls, (Ntt, FftMixed)):
         kw["batch"] = args.batch
     if args.batch is not None and issubclass(cls, RsDecode):
         kw["total"] = args.batch

@@ -350,3 +350,62 @@ def outer(field, a, b, out=None):
     if out is not None:
         raise NotImplementedError("The 'out' argument is not supported by the CUDA backend's outer().")
     return np.multiply.outer(a.ravel(), b.ravel())
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident entry points (no host round trip of the matrix / roots)
+# ------------------------------------------------------------------------------------------------
+def row_reduce_device(A, ncols=None, out=None):
+    """
+    Reduced row echelon form of a device-resident 2-D ``DeviceArray`` (gfb_row_reduce).  ``out`` (same shape/dtype)
+    receives the result; by default a copy of ``A`` is reduced.  Returns ``(out, info, det)`` where ``info`` is a CUDA
+    int64 tensor ``[n_pivots, n_row_exchanges]`` and ``det`` a one-element DeviceArray with the signed pivot product.
+    """
+    import torch
+
+    from ._field import DeviceArray
+
+    field = A.field
+    _no_wide(field, "row_reduce")
+    if len(A.shape) != 2:
+        raise ValueError(f"Only 2-D matrices can be converted to reduced row echelon form, not {len(A.shape)}-D.")
+    rows, cols = A.shape
+    ncols = cols if ncols is None else int(ncols)
+    if out is None:
+        out = DeviceArray(field, A.tensor.clone(), A.shape, A.dtype)
+    elif out is not A:
+        out.tensor.copy_(A.tensor)
+    lib = _lib.lib()
+    ws = torch.empty(lib.gfb_row_reduce_workspace_bytes(field._handle(), rows, cols), dtype=torch.uint8, device="cuda")
+    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    det = DeviceArray.empty(field, (1,), A.dtype)
+    st = lib.gfb_row_reduce(field._handle(), A.elem_bytes, out.data_ptr, rows, cols, ncols, info.data_ptr(), det.data_ptr,
+                            ws.data_ptr(), DeviceArray._stream())
+    _lib.check(st, "gfb_row_reduce")
+    return out, info, det
+
+
+def poly_roots_device(nonzero_degrees, nonzero_coeffs, max_roots=None):
+    """
+    gfb_poly_roots with device-resident coefficients (a 1-D ``DeviceArray``) -> (roots DeviceArray of capacity
+    ``max_roots``, CUDA uint64-as-int64 tensor with the number of roots).
+    """
+    import torch
+
+    from ._field import DeviceArray
+
+    field = nonzero_coeffs.field
+    degrees = np.ascontiguousarray(nonzero_degrees, dtype=np.int64).reshape(-1)
+    if degrees.size == 0 or degrees.size != nonzero_coeffs.size:
+        raise ValueError("Arguments 'nonzero_degrees' and 'nonzero_coeffs' must be non-empty and have the same size.")
+    if np.any(np.diff(degrees) >= 0):
+        raise ValueError("Argument 'nonzero_degrees' must be strictly descending.")
+    max_roots = int(min(int(degrees[0]), field.order)) if max_roots is None else int(max_roots)
+    lib = _lib.lib()
+    ws = torch.empty(lib.gfb_poly_roots_workspace_bytes(field._handle(), degrees.size), dtype=torch.uint8, device="cuda")
+    count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    roots = DeviceArray.empty(field, (max(max_roots, 1),), nonzero_coeffs.dtype)
+    st = lib.gfb_poly_roots(field._handle(), nonzero_coeffs.elem_bytes, degrees.ctypes.data, nonzero_coeffs.data_ptr,
+                            degrees.size, roots.data_ptr, max_roots, count.data_ptr(), ws.data_ptr(), DeviceArray._stream())
+    _lib.check(st, "gfb_poly_roots")
+    return roots, count

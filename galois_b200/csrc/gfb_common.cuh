@@ -98,17 +98,41 @@ struct PrimeBarrett {
     }
     // order - 1 as an unsigned 64-bit integer (exponent modulus)
     __device__ __forceinline__ unsigned long long group_order() const { return (unsigned long long)p - 1ull; }
+    // square-and-multiply inside the Montgomery domain: one montmul per squaring / multiply instead of two
     __device__ __forceinline__ elem pow_u64(elem a, unsigned long long e) const {
-        elem r = one();
+        if (p == 2u) return e == 0ull ? 1u : a;
+        elem x = montmul(a, r2);   // a R
+        elem r = montmul(1u, r2);  // R  (one)
         while (e) {
-            if (e & 1ull) r = mul(r, a);
+            if (e & 1ull) r = montmul(r, x);
             e >>= 1;
-            if (e) a = mul(a, a);
+            if (e) x = montmul(x, x);
         }
-        return r;
+        return montmul(r, 1u);
     }
-    // inverse of a non-zero element (Fermat: a^(p-2))
-    __device__ __forceinline__ elem inv1(elem a) const { return pow_u64(a, (unsigned long long)p - 2ull); }
+    // inverse of a non-zero element (Fermat: a^(p-2)).  Branch-free, fixed 32 rounds in the Montgomery domain: the
+    // multiply chain (r) and the squaring chain (x) are independent, so a lone thread — the pivot inversion of the
+    // Gaussian elimination — sees ~32 x one Montgomery latency instead of a data-dependent loop with two branches
+    // per exponent bit.  Squarings past the top bit are harmless.
+    __device__ __forceinline__ elem inv1(elem a) const {
+        if (p == 2u) return a;
+        elem x = montmul(a, r2);   // a R
+        elem r = montmul(1u, r2);  // R
+        uint32_t e = p - 2u;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const elem t = montmul(r, x);
+            r = (e & 1u) ? t : r;
+            x = montmul(x, x);
+            e >>= 1;
+        }
+        return montmul(r, 1u);
+    }
+    // a multiplier used many times: keep it in Montgomery form so that each product is ONE montmul
+    __device__ __forceinline__ elem premul(elem b) const { return p == 2u ? b : montmul(b, r2); }
+    __device__ __forceinline__ elem mul_prepared(elem a, elem b_prepared) const {
+        return p == 2u ? (a & b_prepared) : montmul(a, b_prepared);
+    }
 };
 
 struct PrimeMersenne31 {
@@ -153,6 +177,8 @@ struct PrimeMersenne31 {
         // a^(2^31 - 3): exponent bits are 29 ones, a zero, a one  → fixed addition chain.
         return pow_u64(a, (unsigned long long)p - 2ull);
     }
+    __device__ __forceinline__ elem premul(elem b) const { return b; }
+    __device__ __forceinline__ elem mul_prepared(elem a, elem b_prepared) const { return mul(a, b_prepared); }
 };
 
 // ----------------------------------------------------------------------------------------
@@ -284,6 +310,8 @@ struct BinaryCalc {
         }
         return sqr(beta);
     }
+    __device__ __forceinline__ elem premul(elem b) const { return b; }
+    __device__ __forceinline__ elem mul_prepared(elem a, elem b_prepared) const { return mul(a, b_prepared); }
 };
 
 // ----------------------------------------------------------------------------------------
@@ -329,6 +357,8 @@ struct BinaryLut {
         return s_exp[idx];
     }
     __device__ __forceinline__ elem inv1(elem a) const { return s_exp[(order - 1u) - (uint32_t)s_log[a]]; }
+    __device__ __forceinline__ elem premul(elem b) const { return b; }
+    __device__ __forceinline__ elem mul_prepared(elem a, elem b_prepared) const { return mul(a, b_prepared); }
 };
 
 // ----------------------------------------------------------------------------------------
@@ -460,6 +490,8 @@ struct Binary128 {
         }
         return sqr(beta);
     }
+    __device__ __forceinline__ elem premul(elem b) const { return b; }
+    __device__ __forceinline__ elem mul_prepared(elem a, elem b_prepared) const { return mul(a, b_prepared); }
 };
 
 // ----------------------------------------------------------------------------------------

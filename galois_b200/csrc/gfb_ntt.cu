@@ -732,8 +732,10 @@ static gfb_status run_mixed_t(gfb_ntt_plan* pl, F f, const T* x, T* y, size_t ba
         return GFB_OK;
     }
     const size_t rows_per_chunk = mixed_rows_per_chunk(pl, (int)sizeof(T));
+    // the two ping-pong buffers are laid out as gfb_ntt_workspace_bytes sized them: min(batch, chunk) rows each
+    const size_t rows_ws = batch < rows_per_chunk ? batch : rows_per_chunk;
     T* A = (T*)workspace;
-    T* B = A ? A + rows_per_chunk * n : nullptr;
+    T* B = A ? A + rows_ws * n : nullptr;
     for (size_t off = 0; off < batch; off += rows_per_chunk) {
         const size_t cnt = batch - off < rows_per_chunk ? batch - off : rows_per_chunk;
         size_t blocks = (n * cnt + 255) / 256;

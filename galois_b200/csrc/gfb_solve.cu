@@ -9,16 +9,27 @@
 // scale, eliminate — because with `ncols` < cols (the [A | I] forms) the rows that reduce to zero on the left carry a
 // right-hand part that depends on that rule (left_null_space reads it).
 //
-// One column = two launches, enqueued back to back with no host round trip; the pivot row number, the skip flag and
-// the running determinant live in device memory:
-//   k_*_pivot     (1 CTA)   find the pivot, swap, scale; publish the pivot row (rowbuf) and the column multipliers (colbuf)
-//   k_eliminate   (grid)    A[r][c] -= colbuf[r] * rowbuf[c] for every other row, columns c >= j only (the pivot row is
-//                           zero to the left of column j), 256 columns x 32 rows per CTA
-// Algorithmic bytes per column step: 2 * rows * (cols - j) * elem_bytes (read + write of the trailing block).
+// row_reduce is BLOCKED: 32 pivot columns (a panel) per pass over the matrix, everything enqueued with no host round
+// trip (pivot row counter, exchange count and running determinant live in device memory):
+//   k_rr_panel         (1 CTA)  the 32 column steps restricted to the rows x 32 slab: pivot search, exchange, scale,
+//                               eliminate — and record, per step, the pivot position, its exchange partner, the pivot
+//                               inverse and the multiplier of every row (M, rows x 32; later exchanges permute it too)
+//   k_rr_panel_w       (grid)   per trailing column: replay the exchanges, solve the 32 x 32 triangular recurrence for the
+//                               scaled pivot-row entries w_s, finish the pivot rows, publish W (32 x cols)
+//   k_rr_panel_update  (grid)   A[r][c] -= sum_s M[r][s] * W[s][c] for every non-pivot row: ONE read + write of the
+//                               trailing block per 32 columns instead of per column
+// Exact field arithmetic makes the blocked order bit-identical to the reference's column-by-column order (the pivot
+// decisions only ever look at fully updated slab columns).  Columns left of the panel are never touched: the pivot rows
+// are zero there.  Algorithmic bytes per panel: 2 * rows * (cols - j0 - 32) * elem_bytes.
+//
+// (P)LU keeps the simple form, two launches per column:
+//   k_lu_pivot    (1 CTA)   find the pivot, exchange; publish the pivot row (rowbuf) and the column multipliers (colbuf)
+//   k_eliminate   (grid)    A[r][c] -= colbuf[r] * rowbuf[c] for the rows below, columns c >= i, 256 columns x 32 rows per CTA
 #include <climits>
 
 #include "gfb_common.cuh"
 #include "gfb_dispatch.cuh"
+#include "gfb_dot.cuh"
 
 namespace gfb {
 
@@ -67,49 +78,282 @@ __device__ __forceinline__ int first_nonzero(const T* __restrict__ A, size_t row
     return *s_min;
 }
 
-// ---------------------------------------------------------------------------------------- row_reduce: pivot step
-template <typename T, typename F>
+// ---------------------------------------------------------------------------------------- row_reduce: blocked form
+constexpr int kPanel = 32;
+
+struct PanelMeta {
+    int piv_p[kPanel];                // pivot position of step s, -1 when column j0 + s has no pivot
+    int piv_i[kPanel];                // the row it was exchanged with (== piv_p when no exchange)
+    unsigned long long pinv[kPanel];  // inverse of the pivot
+    int p0, p1;                       // this panel's pivot rows are [p0, p1)
+    int pad[2];
+};
+
+// The slab (rows x kw entries of the panel columns) is staged in shared memory when it fits (SMEM = true, row stride
+// kSlabStride = 33 words: the column scans and the per-row updates are both bank-conflict free); otherwise it stays in
+// global memory and each row segment is updated through fully unrolled, independent loads.
+constexpr int kSlabStride = kPanel + 1;
+
+template <typename T, typename F, bool SMEM>
 __global__ void __launch_bounds__(kPivotThreads)
-k_rr_pivot(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j, ElimState* st, typename F::elem* rowbuf,
-           typename F::elem* colbuf, size_t fs) {
+k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, ElimState* st, PanelMeta* meta,
+           typename F::elem* __restrict__ M, size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    T* s_slab = reinterpret_cast<T*>(reinterpret_cast<char*>(smem_raw) + fs);
+    __shared__ int s_min;
+    __shared__ E s_prow[kPanel];
+    __shared__ E s_pinv;
+    auto at = [&](size_t r, int t) -> T& {
+        if constexpr (SMEM)
+            return s_slab[r * kSlabStride + t];
+        else
+            return A[r * cols + j0 + t];
+    };
+    if constexpr (SMEM) {
+        for (size_t idx = threadIdx.x; idx < rows * (size_t)kw; idx += blockDim.x) {
+            const size_t r = idx / kw;
+            const int t = (int)(idx - r * kw);
+            s_slab[r * kSlabStride + t] = A[r * cols + j0 + t];
+        }
+    }
+    int p = st->p;
+    const int p0 = p;
+    E det = (E)st->det;
+    int swaps = 0;
+    __syncthreads();
+    for (int s = 0; s < kw; ++s) {
+        // first non-zero entry of column s of the slab at or below row p (p is uniform across the CTA)
+        int i = INT_MAX;
+        if ((size_t)p < rows) {
+            if (threadIdx.x == 0) s_min = INT_MAX;
+            __syncthreads();
+            int cand = INT_MAX;
+            for (size_t r = (size_t)p + threadIdx.x; r < rows; r += blockDim.x) {
+                if (at(r, s) != (T)0) {
+                    cand = (int)r;
+                    break;  // later rows of this thread are larger
+                }
+            }
+            cand = __reduce_min_sync(0xffffffffu, cand);  // one shared-memory atomic per warp, not per row
+            if ((threadIdx.x & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
+            __syncthreads();
+            i = s_min;
+        }
+        if (i == INT_MAX) {  // no pivot in this column (or every row already has one): a null step
+            for (size_t r = threadIdx.x; r < rows; r += blockDim.x) M[r * kPanel + s] = f.zero();
+            if (threadIdx.x == 0) meta->piv_p[s] = -1;
+            __syncthreads();  // s_min is rewritten by the next step
+            continue;
+        }
+        const E piv = to_elem<E, T>(at(i, s));
+        __syncthreads();  // the pivot has been read by everyone before row i moves
+        // thread 0 inverts the pivot (a ~45-multiply dependent chain) while warps 1 and 2 exchange rows p and i of the
+        // slab and of the multipliers recorded by the earlier steps
+        if (threadIdx.x == 0) {
+            s_pinv = f.inv1(piv);
+        } else if (i != p && threadIdx.x >= 32 && threadIdx.x < 96) {
+            const int t = (threadIdx.x & 31);
+            if (threadIdx.x < 64) {
+                if (t < kw) {
+                    const T a = at(p, t);
+                    at(p, t) = at(i, t);
+                    at(i, t) = a;
+                }
+            } else if (t < s) {
+                const E a = M[(size_t)p * kPanel + t];
+                M[(size_t)p * kPanel + t] = M[(size_t)i * kPanel + t];
+                M[(size_t)i * kPanel + t] = a;
+            }
+        }
+        __syncthreads();
+        const E pinv = s_pinv;
+        if ((int)threadIdx.x < kw) {  // row p /= pivot (its entries left of column j0 + s are already zero)
+            const E v = f.mul(to_elem<E, T>(at(p, threadIdx.x)), pinv);
+            s_prow[threadIdx.x] = f.premul(v);  // multiplier form: one reduction per product below
+            at(p, threadIdx.x) = to_store<T, E>(v);
+        }
+        __syncthreads();
+        for (size_t r = threadIdx.x; r < rows; r += blockDim.x) {
+            E m = f.zero();
+            if (r != (size_t)p) {
+                m = to_elem<E, T>(at(r, s));
+                if (!f.is_zero(m)) {
+#pragma unroll 4
+                    for (int t = s; t < kw; ++t)
+                        at(r, t) = to_store<T, E>(f.sub(to_elem<E, T>(at(r, t)), f.mul_prepared(m, s_prow[t])));
+                }
+            }
+            M[r * kPanel + s] = m;
+        }
+        if (threadIdx.x == 0) {
+            meta->piv_p[s] = p;
+            meta->piv_i[s] = i;
+            meta->pinv[s] = (unsigned long long)pinv;
+        }
+        det = f.mul(det, piv);
+        swaps += i != p ? 1 : 0;
+        ++p;
+        __syncthreads();
+    }
+    if constexpr (SMEM) {
+        for (size_t idx = threadIdx.x; idx < rows * (size_t)kw; idx += blockDim.x) {
+            const size_t r = idx / kw;
+            const int t = (int)(idx - r * kw);
+            A[r * cols + j0 + t] = s_slab[r * kSlabStride + t];
+        }
+    }
+    if (threadIdx.x == 0) {
+        st->p = p;
+        st->det = (unsigned long long)det;
+        st->n_swaps += swaps;
+        meta->p0 = p0;
+        meta->p1 = p;
+    }
+}
+
+constexpr int kPanelWThreads = 128;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kPanelWThreads)
+k_rr_panel_w(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw, const PanelMeta* __restrict__ meta,
+             const typename F::elem* __restrict__ M, typename F::elem* __restrict__ W, size_t fs) {
     using E = typename F::elem;
     extern __shared__ uint4 smem_raw[];
     f.init_smem(smem_raw);
     (void)fs;
-    __shared__ int s_min;
-    const int p = st->p;
-    if ((size_t)p >= rows) {  // every row already holds a pivot (`if p == A_rre.shape[0]: break`)
-        __syncthreads();
-        if (threadIdx.x == 0) st->skip = 1;
-        return;
+    (void)rows;
+    __shared__ E s_mp[kPanel][kPanel + 1];  // s_mp[s][t] = multiplier of pivot row s at step t
+    __shared__ int s_p[kPanel], s_i[kPanel];
+    __shared__ E s_pinv[kPanel];
+    __shared__ int s_pos[2 * kPanel], s_src[2 * kPanel], s_moves;
+    __shared__ E s_w[kPanel][kPanelWThreads];
+    if (meta->p1 == meta->p0) return;  // the panel found no pivot: nothing changes (uniform)
+    for (int idx = threadIdx.x; idx < kPanel * kPanel; idx += blockDim.x) {
+        const int s = idx / kPanel, t = idx - s * kPanel;
+        const int ps = s < kw ? meta->piv_p[s] : -1;
+        s_mp[s][t] = (ps >= 0 && t < kw) ? M[(size_t)ps * kPanel + t] : f.zero();
     }
-    const int i = first_nonzero(A, rows, cols, j, p, &s_min);
-    if (i == INT_MAX) {  // `if idxs.size == 0: continue`
-        if (threadIdx.x == 0) st->skip = 1;
-        return;
+    if (threadIdx.x < kPanel) {
+        const int s = threadIdx.x;
+        s_p[s] = s < kw ? meta->piv_p[s] : -1;
+        s_i[s] = s < kw ? meta->piv_i[s] : -1;
+        s_pinv[s] = s < kw ? (E)meta->pinv[s] : f.zero();
     }
-    const E piv = to_elem<E, T>(A[(size_t)i * cols + j]);
-    const E pinv = f.inv1(piv);
-    __syncthreads();  // everyone has read the pivot before row i is overwritten
-    // swap rows p and i, then row p /= pivot
-    for (size_t c = threadIdx.x; c < cols; c += blockDim.x) {
-        const T vi = A[(size_t)i * cols + c];
-        const T vp = A[(size_t)p * cols + c];
-        const E nv = f.mul(to_elem<E, T>(vi), pinv);
-        rowbuf[c] = nv;
-        A[(size_t)p * cols + c] = to_store<T, E>(nv);
-        if (i != p) A[(size_t)i * cols + c] = vp;
+    // Net effect of the panel's row exchanges as a move list (built once per CTA): position s_pos[k] ends up holding
+    // the row that started at s_src[k].  Every thread then moves its own column with independent loads and stores
+    // instead of replaying up to 32 dependent exchanges.
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int s = 0; s < kw; ++s) {
+            const int ps = s < kw ? meta->piv_p[s] : -1;
+            const int is = ps >= 0 ? meta->piv_i[s] : -1;
+            if (ps < 0 || is == ps) continue;
+            int kp = -1, ki = -1;
+            for (int k = 0; k < n; ++k) {
+                if (s_pos[k] == ps) kp = k;
+                if (s_pos[k] == is) ki = k;
+            }
+            if (kp < 0) {
+                kp = n++;
+                s_pos[kp] = ps;
+                s_src[kp] = ps;
+            }
+            if (ki < 0) {
+                ki = n++;
+                s_pos[ki] = is;
+                s_src[ki] = is;
+            }
+            const int a = s_src[kp];
+            s_src[kp] = s_src[ki];
+            s_src[ki] = a;
+        }
+        s_moves = n;
     }
     __syncthreads();
-    // multipliers of every other row: their entry in column j (after the swap)
-    for (size_t r = threadIdx.x; r < rows; r += blockDim.x)
-        colbuf[r] = r == (size_t)p ? f.zero() : to_elem<E, T>(A[r * cols + j]);
-    if (threadIdx.x == 0) {
-        st->cur_p = p;
-        st->p = p + 1;
-        st->skip = 0;
-        st->det = (unsigned long long)f.mul((E)st->det, piv);
-        if (i != p) st->n_swaps += 1;
+    const size_t c = c0 + (size_t)blockIdx.x * kPanelWThreads + threadIdx.x;
+    if (c >= cols) return;
+    {
+        const int n = s_moves;
+        T v[2 * kPanel];
+        for (int k = 0; k < n; ++k) v[k] = A[(size_t)s_src[k] * cols + c];
+        for (int k = 0; k < n; ++k)
+            if (s_src[k] != s_pos[k]) A[(size_t)s_pos[k] * cols + c] = v[k];
+    }
+    // w_s = pinv_s * (x[p_s] - sum_{t<s} M[p_s][t] w_t): the entry of the scaled pivot row at the moment step s used it.
+    // Rolled loops over a per-thread column of shared memory (s_w[.][tid]): fully unrolling the 32 x 32 recurrence makes
+    // ~230 KB of straight-line code that runs at instruction-fetch speed.
+    const int tid = threadIdx.x;
+#pragma unroll 8
+    for (int s = 0; s < kw; ++s) s_w[s][tid] = to_elem<E, T>(A[(size_t)(s_p[s] >= 0 ? s_p[s] : 0) * cols + c]);
+#pragma unroll 1
+    for (int s = 0; s < kw; ++s) {
+        E ws = f.zero();
+        if (s_p[s] >= 0) {
+            DotAcc<F> acc;
+            acc.init(f);
+#pragma unroll 4
+            for (int t = 0; t < s; ++t) acc.fma(f, s_mp[s][t], s_w[t][tid]);
+            ws = f.mul(s_pinv[s], f.sub(s_w[s][tid], acc.done(f)));
+        }
+        s_w[s][tid] = ws;
+    }
+    // the pivot rows end as w_s minus what the later steps subtracted from them
+#pragma unroll 1
+    for (int s = 0; s < kw; ++s) {
+        if (s_p[s] >= 0) {
+            DotAcc<F> acc;
+            acc.init(f);
+#pragma unroll 4
+            for (int t = s + 1; t < kw; ++t) acc.fma(f, s_mp[s][t], s_w[t][tid]);
+            A[(size_t)s_p[s] * cols + c] = to_store<T, E>(f.sub(s_w[s][tid], acc.done(f)));
+        }
+    }
+#pragma unroll 4
+    for (int s = 0; s < kw; ++s) W[(size_t)s * cols + c] = s_w[s][tid];
+}
+
+constexpr int kUpdCols = 128;
+constexpr int kUpdRows = 16;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kUpdCols)
+k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw,
+                  const PanelMeta* __restrict__ meta, const typename F::elem* __restrict__ M,
+                  const typename F::elem* __restrict__ W, size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    __shared__ E s_m[kUpdRows][kPanel];
+    const int p0 = meta->p0, p1 = meta->p1;
+    if (p1 == p0) return;  // uniform
+    const size_t r0 = (size_t)blockIdx.y * kUpdRows;
+    for (int idx = threadIdx.x; idx < kUpdRows * kPanel; idx += blockDim.x) {
+        const int rr = idx / kPanel, t = idx - rr * kPanel;
+        const size_t r = r0 + rr;
+        s_m[rr][t] = (r < rows && t < kw) ? M[r * kPanel + t] : f.zero();
+    }
+    __syncthreads();
+    const size_t c = c0 + (size_t)blockIdx.x * kUpdCols + threadIdx.x;
+    if (c >= cols) return;
+    E w[kPanel];
+#pragma unroll
+    for (int t = 0; t < kPanel; ++t) w[t] = t < kw ? W[(size_t)t * cols + c] : f.zero();
+    for (int rr = 0; rr < kUpdRows; ++rr) {
+        const size_t r = r0 + rr;
+        if (r >= rows) break;
+        if (r >= (size_t)p0 && r < (size_t)p1) continue;  // pivot rows were finished by k_rr_panel_w
+        DotAcc<F> acc;
+        acc.init(f);
+#pragma unroll
+        for (int t = 0; t < kPanel; ++t) acc.fma(f, s_m[rr][t], w[t]);
+        const E d = acc.done(f);
+        if (!f.is_zero(d)) {
+            const size_t idx = r * cols + c;
+            A[idx] = to_store<T, E>(f.sub(to_elem<E, T>(A[idx]), d));
+        }
     }
 }
 
@@ -242,15 +486,33 @@ struct ElimWorkspace {
     ElimState* state;
     void* rowbuf;
     void* colbuf;
+    PanelMeta* meta;
+    void* M;  // rows x kPanel multipliers
+    void* W;  // kPanel x cols scaled pivot-row entries
 };
 
-static ElimWorkspace carve(void* ws, size_t cols) {
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+static ElimWorkspace carve(void* ws, size_t rows, size_t cols) {
     char* base = (char*)ws;
     ElimWorkspace w;
     w.state = (ElimState*)base;
-    w.rowbuf = base + 64;
-    w.colbuf = base + 64 + ((cols * 8 + 15) & ~(size_t)15);
+    base += 64;
+    w.rowbuf = base;
+    base += align16(cols * 8);
+    w.colbuf = base;
+    base += align16(rows * 8);
+    w.meta = (PanelMeta*)base;
+    base += align16(sizeof(PanelMeta));
+    w.M = base;
+    base += align16(rows * kPanel * 8);
+    w.W = base;
     return w;
+}
+
+static size_t elim_workspace_bytes(size_t rows, size_t cols) {
+    return 64 + align16(cols * 8) + align16(rows * 8) + align16(sizeof(PanelMeta)) + align16(rows * kPanel * 8) +
+           align16(cols * kPanel * 8) + 64;
 }
 
 static dim3 elim_grid(size_t rows, size_t cols, size_t c0) {
@@ -263,7 +525,7 @@ extern "C" {
 
 size_t gfb_row_reduce_workspace_bytes(const gfb_field* f, size_t rows, size_t cols) {
     (void)f;
-    return 64 + ((cols * 8 + 15) & ~(size_t)15) + rows * 8 + 64;
+    return gfb::elim_workspace_bytes(rows, cols);
 }
 
 gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t cols, size_t ncols, int64_t* d_info,
@@ -280,14 +542,33 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
         using T = typename decltype(tag)::type;
         using E = typename F::elem;
         const size_t fs = field_smem_bytes(functor);
-        ElimWorkspace w = carve(d_workspace, cols);
+        ElimWorkspace w = carve(d_workspace, rows, cols);
         k_elim_init<F><<<1, 32, fs, st>>>(functor, w.state, fs);
         if (rows && cols) {
-            for (size_t j = 0; j < ncols; ++j) {
-                k_rr_pivot<T, F><<<1, kPivotThreads, fs, st>>>(functor, (T*)A, rows, cols, j, w.state, (E*)w.rowbuf,
-                                                                (E*)w.colbuf, fs);
-                k_eliminate<T, F><<<elim_grid(rows, cols, j), kElimCols, fs, st>>>(
-                    functor, (T*)A, rows, cols, j, w.state, (const E*)w.rowbuf, (const E*)w.colbuf, fs);
+            if ((rows + kUpdRows - 1) / kUpdRows > 65535) return GFB_ERR_UNSUPPORTED;
+            // the panel slab lives in shared memory when rows * 33 entries fit beside the field tables
+            const size_t slab_bytes = align16(rows * kSlabStride * sizeof(T));
+            const bool slab_in_smem = fs + slab_bytes <= (size_t)200 * 1024;
+            if (slab_in_smem)
+                GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)(fs + slab_bytes)));
+            for (size_t j0 = 0; j0 < ncols; j0 += kPanel) {
+                const int kw = (int)(ncols - j0 < (size_t)kPanel ? ncols - j0 : (size_t)kPanel);
+                if (slab_in_smem)
+                    k_rr_panel<T, F, true><<<1, kPivotThreads, fs + slab_bytes, st>>>(functor, (T*)A, rows, cols, j0, kw,
+                                                                                       w.state, w.meta, (E*)w.M, fs);
+                else
+                    k_rr_panel<T, F, false><<<1, kPivotThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
+                                                                           w.meta, (E*)w.M, fs);
+                const size_t c0 = j0 + kw;  // trailing columns
+                if (c0 < cols) {
+                    const unsigned gw = (unsigned)((cols - c0 + kPanelWThreads - 1) / kPanelWThreads);
+                    k_rr_panel_w<T, F><<<gw, kPanelWThreads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                       (const E*)w.M, (E*)w.W, fs);
+                    dim3 gu((unsigned)((cols - c0 + kUpdCols - 1) / kUpdCols), (unsigned)((rows + kUpdRows - 1) / kUpdRows));
+                    k_rr_panel_update<T, F><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                      (const E*)w.M, (const E*)w.W, fs);
+                }
             }
         }
         k_elim_report<T, F><<<1, 32, fs, st>>>(functor, w.state, (long long*)d_info, (T*)d_det, 0, fs);
@@ -308,7 +589,7 @@ gfb_status gfb_plu_decompose(gfb_field* f, int eb, void* A, void* L, int64_t* d_
         using T = typename decltype(tag)::type;
         using E = typename F::elem;
         const size_t fs = field_smem_bytes(functor);
-        ElimWorkspace w = carve(d_workspace, cols);
+        ElimWorkspace w = carve(d_workspace, rows, cols);
         k_elim_init<F><<<1, 32, fs, st>>>(functor, w.state, fs);
         size_t blocks = (rows * rows + 255) / 256;
         if (blocks > 4096) blocks = 4096;

@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 OUT=gpurun_out/${TAG}_bench_all.jsonl
 mkdir -p gpurun_out; : > $OUT
-for wl in gfp_mul gfp_add gfp_inv gfp_div gfp_mul_u32 gfp_mul_barrett gf256_mul_1e6 gf256_mul gf2_32_mul ntt intt gf2_128_mul gf2_128_inv rs_encode rs_decode rs_decode_erasures bch_decode; do
+for wl in gfp_mul gfp_add gfp_inv gfp_div gfp_mul_u32 gfp_mul_barrett gf256_mul_1e6 gf256_mul gf2_32_mul ntt intt gf2_128_mul gf2_128_inv rs_encode rs_decode rs_decode_erasures bch_decode matinv poly_roots fft_mixed; do
     extra=""
     case $wl in ntt|intt) extra="--batch 1036";; esac
     timeout 600 python bench.py --workload $wl --steps 20 --warmup 3 --no-extras $extra 2>gpurun_out/${TAG}_err_$wl.log | tail -1 >> $OUT

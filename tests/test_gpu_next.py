@@ -289,3 +289,45 @@ def test_dot_family_matches_oracle():
     A, B = GF.Random((9, 50), seed=3), GF.Random((50, 4), seed=4)
     assert eq(np.dot(A, B), F.matmul(np.asarray(A), np.asarray(B)))
     assert eq(np.dot(A, a), F.matmul(np.asarray(A), np.asarray(a).reshape(-1, 1)).reshape(-1))
+
+
+def test_fft_mixed_host_pipeline_many_chunks():
+    """A host batch larger than one staging chunk (32 MiB): every chunk gets its own, smaller workspace layout."""
+    GF = gb.GF(998244353)
+    F = oracle.Field.prime(998244353)
+    n = 7 * 17 * 2**13
+    x = GF.Random((19, n), seed=5)
+    X = np.fft.fft(x)
+    omega = int(GF.primitive_root_of_unity(n))
+    for row in (0, 7, 8, 18):
+        assert eq(X[row], F.fft(np.asarray(x[row]), omega)), row
+    assert eq(np.fft.ifft(X), x)
+
+
+def test_row_reduce_panel_edges():
+    """Shapes around the 32-column panel and 64-row tile boundaries, rank-deficient panels, device-resident entry."""
+    from galois_b200 import _linalg
+
+    rng = np.random.default_rng(8)
+    GF = gb.GF(3191)
+    F = oracle.Field.prime(3191)
+    for rows, cols, ncols in [(31, 33, None), (32, 32, None), (33, 95, 40), (65, 64, None), (100, 130, 64), (70, 200, 33),
+                              (5, 300, None), (300, 5, None), (129, 129, 128)]:
+        A = rng.integers(0, 3191, (rows, cols))
+        A[:, rng.integers(0, cols, 3)] = 0                # zero columns: null steps inside a panel
+        A[rng.integers(0, rows, 2), :] = 0                # zero rows
+        if cols > 40:
+            A[:, 35] = A[:, 2]                            # a dependent column
+        R, p = F.row_reduce(A, ncols)
+        got = GF(A).row_reduce(ncols=ncols)
+        assert eq(got, R), (rows, cols, ncols)
+        dA = GF(A).to_device()
+        out, info, _ = _linalg.row_reduce_device(dA, ncols=ncols)
+        assert eq(out.cpu(), R) and int(info[0].item()) == p
+    # sparse 0/1 matrices over GF(2): many exchanges and null steps
+    G2 = gb.GF(2)
+    F2 = oracle.Field.prime(2)
+    for rows, cols in [(64, 200), (130, 70)]:
+        A = (rng.random((rows, cols)) < 0.05).astype(np.int64)
+        assert eq(G2(A).row_reduce(), F2.row_reduce(A)[0])
+        assert eq(G2(A).left_null_space(), F2.left_null_space(A))
