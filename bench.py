@@ -762,6 +762,7 @@ class MatInv:
         return 1
 
     cpu_sample = "the same 1024x1024 inversion, one thread (row_reduce_jit is a serial NumPy/ufunc loop in the reference)"
+    cpu_cores = 1
 
 
 class PolyRoots:
@@ -830,6 +831,7 @@ class PolyRoots:
 
     cpu_sample = ("2^20 of the 2^31 - 1 points, one thread, Horner evaluation (degree multiplies + adds per point, the "
                   "same count as the reference's Chien step lambda_j *= alpha^j)")
+    cpu_cores = 1
 
 
 class FftMixed:
@@ -965,7 +967,8 @@ def run_reference(args):
         "scaling": cls.scaling, "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
         "config": {"workload": getattr(work, "name", None) or getattr(cls, "name", None) or (cls.__doc__ or cls.__name__).strip().split("\n")[0].rstrip("."),
                    "note": "CPU oracle port of the reference path (oracle/gf_oracle.c); each step is a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": threads, "kind": "port", "sample": cls.cpu_sample},
+        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", threads), "kind": "port",
+                         "sample": cls.cpu_sample},
         "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -1075,7 +1078,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu:
         v, reps, secs, threads = time_cpu(work)
-        cpu = {"value": v, "unit": cls.unit, "cores": threads, "kind": "port",
+        cpu = {"value": v, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", threads), "kind": "port",
                "sample": f"{cls.cpu_sample}; {reps} repetitions in {secs:.1f} s"}
 
     # ---- secondary workloads (default run only): short device-resident timings of the other BASELINE configs

@@ -9,7 +9,7 @@ mkdir -p gpurun_out; : > $OUT
 for wl in $GPU_LIST; do
     extra=""
     case $wl in ntt|intt) extra="--batch 1036";; esac
-    timeout 600 python bench.py --workload $wl --steps 20 --warmup 3 --no-extras $extra 2>>gpurun_out/${TAG}_err_changed.log | tail -1 >> $OUT
+    timeout 600 python bench.py --workload $wl --steps 20 --warmup 3 --no-extras --no-cpu $extra 2>>gpurun_out/${TAG}_err_changed.log | tail -1 >> $OUT
 done
 for wl in $REF_LIST; do
     timeout 600 python bench.py --impl reference --workload $wl --steps 3 --warmup 1 2>>gpurun_out/${TAG}_err_changed.log | tail -1 >> $OUT
