@@ -838,7 +838,7 @@ class FftMixed:
     """mixed-radix DFT, N = 7 * 17 * 2^13 = 974848 over GF(998244353) (fft_jit general branch)."""
 
     metric, unit, dtype, scaling = "fft_mixed_974848_per_sec", "FFT/s", "uint32", "weak"
-    kernel = "k_mixed_stage (15 stages: 2 x13, 7, 17)"
+    kernel = "k_mixed_stage_v (radix 17, radix 7 + twiddle) -> 8192-point four-step kernels on rows -> k_transpose_rows"
     N = 7 * 17 * 2**13
     bytes_per_unit = 2 * 4 * 7 * 17 * 2**13
 
@@ -856,7 +856,8 @@ class FftMixed:
         self.x = gb.DeviceArray(self.GF, x.view(torch.uint8).reshape(-1), (self.rows, self.N), np.uint32)
         self.out = gb.DeviceArray.empty(self.GF, (self.rows, self.N), np.uint32)
         self.units_per_step = self.rows
-        self.launches_per_step = 15 * ((self.rows * self.N * 4 + (64 << 20) - 1) // (64 << 20))
+        chunk_rows = max(1, (64 << 20) // (self.N * 4))  # rows per workspace chunk (gfb_ntt.cu: kGenericWsBytes)
+        self.launches_per_step = 5 * ((self.rows + chunk_rows - 1) // chunk_rows)  # 2 odd stages, 2 row passes, permutation
         self.h2d = self.d2h = 0
 
     def step(self):

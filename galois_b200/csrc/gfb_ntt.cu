@@ -48,6 +48,10 @@ struct gfb_ntt_plan {
     uint32_t factors[32];  // prime factors of N with multiplicity, ascending (fft_jit._prime_factors)
     uint64_t omega64, scale64;
     void* d_pow_mixed;     // omega^e, e < N, in the field's compute element type
+    // hybrid N = n_odd * 2^k (k >= 5, p < 2^31): odd radices on columns, then the power-of-two kernels on rows
+    gfb_ntt_plan* sub;     // plan of size n_pow2 with omega^n_odd (and the caller's scale)
+    size_t n_odd, n_pow2;
+    int n_odd_factors;     // the odd entries of factors[] (they follow the 2s)
 };
 
 namespace gfb {
@@ -171,12 +175,66 @@ k_mixed_stage(F f, const T* __restrict__ in, T* __restrict__ out, const typename
         const size_t rem = o - qi * rm;  // fo*m + b
         const size_t b = rem % m;
         const T* src = in + row * n + qi * m + b;
-        const E tw = pow[q * rem];       // q * rem < q*r*m = n
+        const E tw = f.premul(pow[q * rem]);  // q * rem < q*r*m = n; multiplier form: one reduction per Horner step
         const size_t kstride = q * m;
         E acc = to_elem<E, T>(src[(r - 1) * kstride]);
-        for (size_t k = r - 1; k-- > 0;) acc = f.add(f.mul(acc, tw), to_elem<E, T>(src[k * kstride]));
+        for (size_t k = r - 1; k-- > 0;) acc = f.add(f.mul_prepared(acc, tw), to_elem<E, T>(src[k * kstride]));
         if (apply_scale) acc = f.mul(acc, scale);
         out[idx] = to_store<T, E>(acc);
+    }
+}
+
+// Hybrid form, N = N1 * V with V = 2^k: the same radix-r stage applied along axis 0 of each row viewed as [N1][V]
+// (lane index v runs along the contiguous axis: coalesced), omega_N1 = omega^V so the stage twiddle is pow[V * q * rem].
+// The last odd stage also applies the Cooley-Tukey twiddle omega^(k1 * v) between the two factors.
+template <typename T, typename F>
+__global__ void __launch_bounds__(256)
+k_mixed_stage_v(F f, const T* __restrict__ in, T* __restrict__ out, const typename F::elem* __restrict__ pow, size_t n1,
+                size_t V, size_t m, size_t r, size_t batch, int fuse_twiddle, size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    const size_t n = n1 * V;
+    const size_t total = n * batch;
+    const size_t q = n1 / (m * r);
+    const size_t rm = r * m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = idx / n;
+        const size_t within = idx - row * n;
+        const size_t o = within / V;  // output index along axis 0 (k1 after the last stage)
+        const size_t v = within - o * V;
+        const size_t qi = o / rm;
+        const size_t rem = o - qi * rm;  // fo*m + b
+        const size_t b = rem % m;
+        const T* src = in + row * n + (qi * m + b) * V + v;
+        const E tw = f.premul(pow[q * rem * V]);  // multiplier form: one reduction per Horner step
+        const size_t kstride = q * m * V;
+        E acc = to_elem<E, T>(src[(r - 1) * kstride]);
+        for (size_t k = r - 1; k-- > 0;) acc = f.add(f.mul_prepared(acc, tw), to_elem<E, T>(src[k * kstride]));
+        if (fuse_twiddle) acc = f.mul(acc, pow[o * v]);  // o * v < N1 * V = N
+        out[idx] = to_store<T, E>(acc);
+    }
+}
+
+// out[row][k2 * n1 + k1] = in[row][k1 * V + k2]: the output permutation of the two-factor split, 32 x 32 tiles
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose_rows(const T* __restrict__ in, T* __restrict__ out, size_t n1, size_t V) {
+    __shared__ T tile[32][33];
+    const size_t row = blockIdx.z;
+    const T* src = in + row * n1 * V;
+    T* dst = out + row * n1 * V;
+    const size_t k2_0 = (size_t)blockIdx.x * 32, k1_0 = (size_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const size_t k1 = k1_0 + j, k2 = k2_0 + tx;
+        if (k1 < n1 && k2 < V) tile[j][tx] = src[k1 * V + k2];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const size_t k2 = k2_0 + j, k1 = k1_0 + tx;
+        if (k1 < n1 && k2 < V) dst[k2 * n1 + k1] = tile[tx][j];
     }
 }
 
@@ -714,8 +772,56 @@ static gfb_status run_generic_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch
 }
 
 static size_t mixed_rows_per_chunk(const gfb_ntt_plan* pl, int eb) {
-    const size_t rows = kGenericWsBytes / (pl->n * (size_t)eb);
+    size_t rows = kGenericWsBytes / (pl->n * (size_t)eb);
+    if (rows > 32768) rows = 32768;  // the row index is a grid dimension in the output permutation
     return rows ? rows : 1;
+}
+
+extern "C" gfb_status gfb_ntt_exec(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t batch, void* workspace,
+                                   void* stream);
+extern "C" size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t batch);
+
+// N = n_odd * 2^k: odd radices down the columns (+ inter-factor twiddle), the power-of-two kernels along the rows,
+// then the [n_odd][2^k] -> [2^k][n_odd] output permutation.  Workspace: two row buffers + the sub-plan's scratch.
+template <typename T, typename F>
+static gfb_status run_hybrid_t(gfb_ntt_plan* pl, F f, const T* x, T* y, size_t batch, void* workspace, cudaStream_t st) {
+    using E = typename F::elem;
+    const size_t n = pl->n, n1 = pl->n_odd, V = pl->n_pow2;
+    const size_t fs = field_smem_bytes(f);
+    const E* pow = (const E*)pl->d_pow_mixed;
+    const size_t rows_per_chunk = mixed_rows_per_chunk(pl, (int)sizeof(T));
+    const size_t rows_ws = batch < rows_per_chunk ? batch : rows_per_chunk;
+    T* A = (T*)workspace;
+    T* B = A + rows_ws * n;
+    void* sub_ws = (void*)(B + rows_ws * n);
+    const int S = pl->n_odd_factors;
+    for (size_t off = 0; off < batch; off += rows_per_chunk) {
+        const size_t cnt = batch - off < rows_per_chunk ? batch - off : rows_per_chunk;
+        size_t blocks = (n * cnt + 255) / 256;
+        const size_t cap = (size_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        const T* src = x + off * n;
+        T* bufs[2] = {A, B};
+        int cur = 0;
+        size_t m = 1;
+        for (int s = 0; s < S; ++s) {
+            const size_t r = pl->factors[pl->n_factors - 1 - s];  // the odd radices sit at the end: largest first
+            T* dst = bufs[cur];
+            k_mixed_stage_v<T, F><<<(unsigned)blocks, 256, fs, st>>>(f, src, dst, pow, n1, V, m, r, cnt, s == S - 1, fs);
+            src = dst;
+            cur ^= 1;
+            m *= r;
+        }
+        // rows of length V through the power-of-two plan (cnt * n1 independent transforms), into the other buffer
+        T* rows_out = bufs[cur];
+        gfb_status stt = gfb_ntt_exec(pl->sub, (int)sizeof(T), src, rows_out, cnt * n1, sub_ws, (void*)st);
+        if (stt != GFB_OK) return stt;
+        dim3 grid((unsigned)((V + 31) / 32), (unsigned)((n1 + 31) / 32), (unsigned)cnt);
+        if (cnt > 65535 || grid.y > 65535) return GFB_ERR_UNSUPPORTED;
+        k_transpose_rows<T><<<grid, 256, 0, st>>>(rows_out, y + off * n, n1, V);
+    }
+    GFB_CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
 }
 
 template <typename T, typename F>
@@ -725,6 +831,7 @@ static gfb_status run_mixed_t(gfb_ntt_plan* pl, F f, const T* x, T* y, size_t ba
     const size_t fs = field_smem_bytes(f);
     const E scale = (E)pl->scale64;
     const E* pow = (const E*)pl->d_pow_mixed;
+    if (pl->sub) return run_hybrid_t<T, F>(pl, f, x, y, batch, workspace, st);
     const int S = pl->n_factors;
     if (S == 0) {  // N = 1
         k_mixed_scale<T, F><<<(unsigned)((batch + 255) / 256), 256, fs, st>>>(f, x, y, batch, scale, fs);
@@ -853,6 +960,24 @@ gfb_status gfb_ntt_plan_create(gfb_ntt_plan** out, gfb_field* f, size_t n, uint6
             gfb_ntt_plan_destroy(pl);
             return GFB_ERR_BAD_ARG;
         }
+        // N = n_odd * 2^k with 2^k a size the power-of-two kernels take (32 .. 2^20, p < 2^31): hybrid split
+        size_t pow2 = 1;
+        int twos = 0;
+        while (twos < pl->n_factors && pl->factors[twos] == 2) {
+            pow2 <<= 1;
+            ++twos;
+        }
+        if (f->kind == GFB_PRIME && f->p < (1u << 31) && twos >= 5 && twos <= 20 && twos < pl->n_factors) {
+            pl->n_pow2 = pow2;
+            pl->n_odd = n / pow2;
+            pl->n_odd_factors = pl->n_factors - twos;
+            const uint32_t omega_sub = host_powmod((uint32_t)omega, pl->n_odd, f->p);  // order 2^k
+            gfb_status ss = gfb_ntt_plan_create(&pl->sub, f, pow2, omega_sub, scale);
+            if (ss != GFB_OK) {
+                gfb_ntt_plan_destroy(pl);
+                return ss;
+            }
+        }
         *out = pl;
         return GFB_OK;
     }
@@ -930,6 +1055,7 @@ void gfb_ntt_plan_destroy(gfb_ntt_plan* pl) {
     if (pl->d_zt) cudaFree(pl->d_zt);
     if (pl->d_zt1) cudaFree(pl->d_zt1);
     if (pl->d_pow_mixed) cudaFree(pl->d_pow_mixed);
+    if (pl->sub) gfb_ntt_plan_destroy(pl->sub);
     free(pl);
 }
 
@@ -937,9 +1063,12 @@ size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t ba
     using namespace gfb;
     if (!pl || batch == 0) return 0;
     if (pl->mixed) {
-        if (pl->n_factors <= 1) return 0;  // a single stage goes straight from x to y
         const size_t cap = mixed_rows_per_chunk(pl, elem_bytes);
-        return 2 * (batch < cap ? batch : cap) * pl->n * (size_t)elem_bytes;
+        const size_t rows = batch < cap ? batch : cap;
+        if (pl->sub)  // hybrid: two row buffers + the power-of-two plan's scratch for rows * n_odd transforms
+            return 2 * rows * pl->n * (size_t)elem_bytes + gfb_ntt_workspace_bytes(pl->sub, elem_bytes, rows * pl->n_odd);
+        if (pl->n_factors <= 1) return 0;  // a single stage goes straight from x to y
+        return 2 * rows * pl->n * (size_t)elem_bytes;
     }
     if (pl->fast) {
         if (pl->log_n <= 10) return 0;  // single kernel
@@ -962,7 +1091,7 @@ gfb_status gfb_ntt_exec(gfb_ntt_plan* pl, int eb, const void* x, void* y, size_t
     if (gfb_ntt_workspace_bytes(pl, eb, batch) != 0 && !workspace) return GFB_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (pl->mixed) {
-        if (pl->n_factors == 1 && x == y) return GFB_ERR_BAD_ARG;  // one out-of-place stage
+        if (!pl->sub && pl->n_factors == 1 && x == y) return GFB_ERR_BAD_ARG;  // one out-of-place stage
         return run_mixed(pl, eb, x, y, batch, workspace, st);
     }
     if (pl->fast) {

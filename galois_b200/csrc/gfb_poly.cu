@@ -12,6 +12,8 @@
 //
 // The polynomial is sparse: f(x) = sum_j c_j x^(d_j), d_0 > d_1 > ...; Horner over the non-zero terms multiplies by
 // x^(d_{j-1} - d_j) (a plain multiply when the gap is 1, i.e. the dense case).
+#include <type_traits>
+
 #include "gfb_common.cuh"
 #include "gfb_dispatch.cuh"
 
@@ -22,7 +24,7 @@ constexpr int kRootsRounds = 16;                             // elements per thr
 constexpr int kRootsTile = kRootsThreads * kRootsRounds;     // elements per CTA
 constexpr int kRootsChunk = 512;                             // terms staged in shared memory at a time
 
-template <typename T, typename F, bool WRITE>
+template <typename T, typename F, bool WRITE, bool DENSE>
 __global__ void __launch_bounds__(kRootsThreads)
 k_roots(F f, const T* __restrict__ coeffs, const unsigned long long* __restrict__ gaps, size_t n_terms,
         unsigned long long tail_exp, int tail_positive, unsigned long long order, unsigned long long tile0,
@@ -61,11 +63,18 @@ k_roots(F f, const T* __restrict__ coeffs, const unsigned long long* __restrict_
                 }
                 __syncthreads();
             }
-            // acc = acc * x^gap_j + c_j   (gap_0 = 0 contributes acc = c_0)
-            for (size_t j = 0; j < cnt; ++j) {
-                const unsigned long long g = sg[j];
-                const E xg = g == 1ull ? x : f.pow_u64(x, g);
-                acc = f.add(f.mul(acc, xg), sc[j]);
+            if constexpr (DENSE) {
+                // every gap is 1 (all coefficients present): plain Horner, acc = acc * x + c_j, x in multiplier form
+                const E xp = f.premul(x);
+#pragma unroll 8
+                for (size_t j = 0; j < cnt; ++j) acc = f.add(f.mul_prepared(acc, xp), sc[j]);
+            } else {
+                // acc = acc * x^gap_j + c_j   (gap_0 = 0 contributes acc = c_0)
+                for (size_t j = 0; j < cnt; ++j) {
+                    const unsigned long long g = sg[j];
+                    const E xg = g == 1ull ? x : f.pow_u64(x, g);
+                    acc = f.add(f.mul(acc, xg), sc[j]);
+                }
             }
         }
         bool is_root;
@@ -179,6 +188,8 @@ gfb_status gfb_poly_roots(gfb_field* f, int eb, const int64_t* h_degrees, const 
         const unsigned long long g = (unsigned long long)(h_degrees[j - 1] - h_degrees[j]);
         h_gaps[j] = g % qm1;  // order >= 2, so qm1 >= 1; a reduced gap of 1 takes the plain-multiply path (x^g = x)
     }
+    bool dense = true;  // consecutive degrees: the Horner step is a plain multiply by x (gap_0 = 0 only seeds acc = c_0)
+    for (size_t j = 1; j < n_terms; ++j) dense = dense && (h_degrees[j - 1] - h_degrees[j] == 1);
     const unsigned long long tail = (unsigned long long)h_degrees[n_terms - 1];
     const unsigned long long tail_exp = qm1 ? tail % qm1 : 0;
     cudaError_t e = cudaMemcpyAsync(gaps, h_gaps, n_terms * sizeof(unsigned long long), cudaMemcpyHostToDevice, st);
@@ -196,13 +207,20 @@ gfb_status gfb_poly_roots(gfb_field* f, int eb, const int64_t* h_degrees, const 
         const size_t fs = field_smem_bytes(functor);
         const size_t smem = fs + kRootsChunk * (sizeof(unsigned long long) + sizeof(E));
         // grid.x is limited to 2^31 - 1 tiles: fine up to order 2^33 (2^21 tiles)
-        k_roots<T, F, false><<<(unsigned)tiles, kRootsThreads, smem, st>>>(
-            functor, (const T*)d_coeffs, gaps, n_terms, tail_exp, tail > 0, order, 0ull, counts, offsets, (T*)d_roots,
-            (unsigned long long)max_roots, fs);
-        k_roots_scan<<<1, 1024, 0, st>>>(counts, tiles, offsets, d_n_roots);
-        k_roots<T, F, true><<<(unsigned)tiles, kRootsThreads, smem, st>>>(
-            functor, (const T*)d_coeffs, gaps, n_terms, tail_exp, tail > 0, order, 0ull, counts, offsets, (T*)d_roots,
-            (unsigned long long)max_roots, fs);
+        auto launch = [&](auto dense_tag) {
+            constexpr bool DENSE = decltype(dense_tag)::value;
+            k_roots<T, F, false, DENSE><<<(unsigned)tiles, kRootsThreads, smem, st>>>(
+                functor, (const T*)d_coeffs, gaps, n_terms, tail_exp, tail > 0, order, 0ull, counts, offsets, (T*)d_roots,
+                (unsigned long long)max_roots, fs);
+            k_roots_scan<<<1, 1024, 0, st>>>(counts, tiles, offsets, d_n_roots);
+            k_roots<T, F, true, DENSE><<<(unsigned)tiles, kRootsThreads, smem, st>>>(
+                functor, (const T*)d_coeffs, gaps, n_terms, tail_exp, tail > 0, order, 0ull, counts, offsets, (T*)d_roots,
+                (unsigned long long)max_roots, fs);
+        };
+        if (dense)
+            launch(std::true_type{});
+        else
+            launch(std::false_type{});
         GFB_CUDA_TRY(cudaGetLastError());
         return GFB_OK;
     });

@@ -241,14 +241,14 @@ k_rr_panel_w(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw
         s_i[s] = s < kw ? meta->piv_i[s] : -1;
         s_pinv[s] = s < kw ? (E)meta->pinv[s] : f.zero();
     }
-    // Net effect of the panel's row exchanges as a move list (built once per CTA): position s_pos[k] ends up holding
-    // the row that started at s_src[k].  Every thread then moves its own column with independent loads and stores
-    // instead of replaying up to 32 dependent exchanges.
+    __syncthreads();
+    // Net effect of the panel's row exchanges as a move list (built once per CTA from the shared copies of the step
+    // records): position s_pos[k] ends up holding the row that started at s_src[k].  Every thread then moves its own
+    // column with independent loads and stores instead of replaying up to 32 dependent exchanges.
     if (threadIdx.x == 0) {
         int n = 0;
         for (int s = 0; s < kw; ++s) {
-            const int ps = s < kw ? meta->piv_p[s] : -1;
-            const int is = ps >= 0 ? meta->piv_i[s] : -1;
+            const int ps = s_p[s], is = s_i[s];
             if (ps < 0 || is == ps) continue;
             int kp = -1, ki = -1;
             for (int k = 0; k < n; ++k) {

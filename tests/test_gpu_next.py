@@ -331,3 +331,27 @@ def test_row_reduce_panel_edges():
         A = (rng.random((rows, cols)) < 0.05).astype(np.int64)
         assert eq(G2(A).row_reduce(), F2.row_reduce(A)[0])
         assert eq(G2(A).left_null_space(), F2.left_null_space(A))
+
+
+def test_fft_hybrid_odd_times_power_of_two():
+    """N = n_odd * 2^k with k >= 5: odd radices on columns, then every power-of-two kernel family (single kernel,
+    short-column and tile four-step) on rows, then the output permutation; forward, inverse, 4- and 8-byte elements."""
+    GF = gb.GF(998244353)
+    F = oracle.Field.prime(998244353)
+    for n, batch in [(7 * 32, 5), (17 * 64, 3), (119 * 32, 2), (7 * 1024, 3), (7 * 2048, 3), (119 * 4096, 2), (17 * 2**15, 2),
+                     (7 * 2**17, 2)]:
+        omega = int(GF.primitive_root_of_unity(n))
+        x = GF.Random((batch, n), seed=n)
+        want = F.fft(np.asarray(x), omega, threads=8)
+        X = np.fft.fft(x)
+        assert eq(X, want), n
+        assert eq(np.fft.ifft(X), x), n
+        assert eq(np.fft.fft(x.astype(np.int64)), want), n
+        dx = x.to_device()
+        assert eq(gb.ntt_device(dx).cpu(), want), n
+    # a large batch of small transforms (row chunks larger than one grid dimension)
+    x = GF.Random((70000, 224), seed=3)
+    X = np.fft.fft(x)
+    omega = int(GF.primitive_root_of_unity(224))
+    for row in (0, 32767, 32768, 69999):
+        assert eq(X[row], F.fft(np.asarray(x[row]), omega)), row
