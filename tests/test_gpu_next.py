@@ -355,3 +355,20 @@ def test_fft_hybrid_odd_times_power_of_two():
     omega = int(GF.primitive_root_of_unity(224))
     for row in (0, 32767, 32768, 69999):
         assert eq(X[row], F.fft(np.asarray(x[row]), omega)), row
+
+
+def test_row_reduce_slab_in_global_memory():
+    """More rows than the shared-memory slab holds (8-byte elements: > 775 rows): the panel works on global memory."""
+    GF = gb.GF(998244353)
+    F = oracle.Field.prime(998244353)
+    A = GF.Random((800, 840), seed=77, dtype=np.int64)
+    R, p = F.row_reduce(np.asarray(A), ncols=820)
+    got = A.row_reduce(ncols=820)
+    assert got.dtype == np.int64 and eq(got, R)
+    S = GF.Random((790, 790), seed=78, dtype=np.int64)
+    Si = np.linalg.inv(S)
+    assert eq(S @ Si, np.identity(790))
+    G8 = gb.GF(2**8)
+    B = G8.Random((6300, 40), seed=79)  # one-byte elements: 6300 rows exceed the slab as well
+    F8 = oracle.Field.binary(8, 0x11D, alpha=2)
+    assert eq(B.row_reduce(), F8.row_reduce(np.asarray(B))[0])
