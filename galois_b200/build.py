@@ -91,7 +91,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
         return src.name
 
     if todo:
-        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(todo))) as pool:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, 16, len(todo))) as pool:
             for name in pool.map(compile_one, todo):
                 print(f"[galois_b200.build] compiled {name}", flush=True)
     if todo or not LIB.exists():
