@@ -619,7 +619,16 @@ __global__ void __launch_bounds__(kFastThreads, 2)
 
 // transforms per pass-1 / pass-2 launch pair: 74 * 2^20 elements of uint32 workspace; at N = 2^20 that is
 // 74 * 64 CTAs = 16 full waves of 2 CTAs/SM x 148 SMs
-static size_t fast_chunk(const gfb_ntt_plan* pl) { return (size_t)kNttChunk << (20 - pl->log_n); }
+// Tuning knob (experiments only): GFB_NTT_CHUNK=<transforms of 2^20> overrides the chunk, e.g. 18 keeps the 72 MiB
+// workspace of a chunk inside the 126 MB L2 between the two passes at the price of a ragged last wave.
+static size_t fast_chunk(const gfb_ntt_plan* pl) {
+    static const int base = [] {
+        const char* e = getenv("GFB_NTT_CHUNK");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 1024 ? v : kNttChunk;
+    }();
+    return (size_t)base << (20 - pl->log_n);
+}
 
 static Radix32Roots roots_of(const gfb_ntt_plan* pl) {
     Radix32Roots rt;
