@@ -581,6 +581,7 @@ gfb_status gfb_plu_decompose(gfb_field* f, int eb, void* A, void* L, int64_t* d_
                              int pivoting, int64_t* d_info, void* d_workspace, void* stream) {
     using namespace gfb;
     if (!f || !A || !L || !d_perm || !d_info || !d_workspace || rows == 0 || cols == 0) return GFB_ERR_BAD_ARG;
+    if (!pivoting && rows - 1 > cols) return GFB_ERR_BAD_ARG;  // the diagonal walk of lu_decompose needs rows - 1 <= cols
     if (rows > (size_t)INT_MAX / 2 || cols > (size_t)INT_MAX / 2) return GFB_ERR_UNSUPPORTED;
     if ((rows + kElimRows - 1) / kElimRows > 65535) return GFB_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
