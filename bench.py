@@ -1109,6 +1109,7 @@ def main():
                    "l2": "inputs larger than L2 (no flush needed)", "units_per_gpu_per_step": per_gpu_units},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload, per_gpu_units), "kernel": cls.kernel, "peak_source": peak_src,
+                     "frac_of_nominal": achieved / 8000.0,  # HBM3e nominal 8.0 TB/s, alongside the measured peak
                      "algorithmic_bytes_per_unit": cls.bytes_per_unit,
                      "algorithmic_bytes_per_step": cls.bytes_per_unit * per_gpu_units},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
