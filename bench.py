@@ -3,7 +3,7 @@
 bench.py — headline benchmark of the galois_b200 hot path (driver contract: see the task brief).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gfp_mul|ntt|rs_decode|gf2_128_mul]
-    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (baseline/_ref: galois + Numba) on the host
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Default workload = BASELINE.json configs[1]: GF(2^31-1) element-wise multiply of two 1e8-element int64
@@ -36,6 +36,27 @@ sys.path.insert(0, str(ROOT))
 
 P_M31 = 2**31 - 1
 P_NTT = 998244353
+REF_DIR = ROOT / "baseline" / "_ref"
+PORT_THREADS_CAP = 64  # OpenMP threads of the secondary CPU figure (oracle port): fixed, the same at every N
+
+
+def load_reference():
+    """The unmodified reference (mhostetter/galois installed at baseline/_ref), or None."""
+    if not (REF_DIR / "galois").is_dir():
+        return None
+    if str(REF_DIR) not in sys.path:
+        sys.path.insert(0, str(REF_DIR))
+    os.environ.setdefault("NUMBA_CACHE_DIR", str(ROOT / "baseline" / "_numba_cache"))
+    try:
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            import galois
+        return galois
+    except Exception as exc:  # numba / llvmlite missing
+        print(f"[bench] reference not importable: {type(exc).__name__}: {exc}", file=sys.stderr)
+        return None
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -150,20 +171,28 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
-def time_steps(step_fn, steps: int, warmup: int, world: int):
+def time_steps(step_fn, steps: int, warmup: int, world: int, per_step=None):
     """W untimed warm-ups, then EXACTLY `steps` steps between barrier+synchronize pairs; CUDA events on the
-    current torch stream (the stream every kernel here is launched on).  Returns max-over-ranks milliseconds."""
+    current torch stream (the stream every kernel here is launched on).  Returns max-over-ranks milliseconds of the
+    whole region; `per_step` (a list) receives this rank's per-step durations (events between the steps)."""
     import torch
 
     for _ in range(warmup):
         step_fn()
     barrier_sync(world)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)] if per_step is not None and steps <= 4096 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
+    if marks:
+        marks[0].record()
+    for i in range(steps):
         step_fn()
+        if marks:
+            marks[i + 1].record()
     e1.record()
     barrier_sync(world)
+    if marks:
+        per_step.extend(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
     return max_over_ranks(e0.elapsed_time(e1), world)
 
 
@@ -211,14 +240,49 @@ class GfpMul:
         want = oracle.Field.prime(P_M31).mul(xs, ys)
         assert np.array_equal(got, want), "GPU result differs from the oracle"
 
-    # end-to-end through the public API with host ndarrays
-    def e2e_setup(self):
-        self.hx = self.GF.Random(self.n, seed=1, dtype=np.int64)
-        self.hy = self.GF.Random(self.n, seed=2, low=1, dtype=np.int64)
+    # end-to-end through the reference-facing API with HOST ndarrays: x * y on the reference's own galois.GF(2^31-1)
+    # arrays (ordinary pageable NumPy memory) with galois_b200.enable(GF); the mirror class on pinned arrays is the
+    # second figure
+    def e2e_setup(self, galois=None):
         self.h2d, self.d2h = 2 * 8 * self.n, 8 * self.n
+        self.px = self.GF.Random(self.n, seed=1, dtype=np.int64)
+        self.py = self.GF.Random(self.n, seed=2, low=1, dtype=np.int64)
+        if galois is None:
+            self.hx, self.hy = self.px, self.py
+            self.e2e_api = "galois_b200.GF(2^31-1): x * y on pinned host ndarrays (gfb_binary_host)"
+            return
+        self.RGF = self.gb.enable(galois.GF(P_M31))
+        self.hx = self.RGF.Random(self.n, seed=1, dtype=np.int64)
+        self.hy = self.RGF.Random(self.n, seed=2, low=1, dtype=np.int64)
+        self.e2e_api = ("galois.GF(2^31-1) (the unmodified reference, baseline/_ref) after galois_b200.enable(GF): x * y on "
+                        "pageable host ndarrays -> gfb_binary_host")
 
     def e2e_step(self):
         self.hz = self.hx * self.hy
+
+    def e2e_pinned_step(self):
+        self.pz = self.px * self.py
+
+    def e2e_teardown(self):
+        if hasattr(self, "RGF"):
+            assert type(self.hz) is self.RGF and self.hz.dtype == np.int64
+            import oracle
+
+            want = oracle.Field.prime(P_M31).mul(np.asarray(self.hx[:100000]), np.asarray(self.hy[:100000]))
+            assert np.array_equal(np.asarray(self.hz[:100000]), want), "e2e result differs from the oracle"
+            self.gb.disable(self.RGF)
+
+    # the reference itself: galois.GF(2^31-1), x * y on the full arrays (Numba jit-calculate ufunc, single thread)
+    def ref_setup(self, galois):
+        GF = galois.GF(P_M31)
+        self.rx = GF.Random(self.n, seed=1, dtype=np.int64)
+        self.ry = GF.Random(self.n, seed=2, low=1, dtype=np.int64)
+
+    def ref_step(self):
+        self.rz = self.rx * self.ry
+        return self.n
+
+    ref_sample = "full 1e8-element int64 arrays: x * y on galois.GF(2^31-1) FieldArrays (Numba jit-calculate ufunc, _calculate.py:337-340)"
 
     def cpu_step(self, threads):
         import oracle
@@ -266,6 +330,9 @@ class Ntt:
     def step(self):
         self.gb.ntt_device(self.x, out=self.out)
 
+    def gather_tensor(self):
+        return self.out.tensor.view(self.rows, -1)
+
     def check(self):
         import oracle
 
@@ -275,14 +342,30 @@ class Ntt:
         got = self.out.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
         assert np.array_equal(got, F.fft(row, omega)), "GPU NTT differs from the oracle"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.e2e_rows = min(self.rows, 256)
         self.hx = self.GF.Random((self.e2e_rows, self.N), seed=3)
         self.h2d = self.d2h = 4 * self.N * self.e2e_rows
         self.e2e_units = self.e2e_rows
+        self.e2e_api = "galois_b200.ntt on a pinned [rows, 2^20] host batch (gfb_ntt_exec_host)"
 
     def e2e_step(self):
         self.hz = self.gb.ntt(self.hx)
+
+    # the reference is 1-D only (_function.py:180-181): one galois.ntt call per row, single thread
+    ref_rows = 4
+
+    def ref_setup(self, galois):
+        self.rgalois = galois
+        GF = galois.GF(P_NTT)
+        self.rx = GF.Random((self.ref_rows, self.N), seed=3)
+
+    def ref_step(self):
+        for i in range(self.ref_rows):
+            self.rz = self.rgalois.ntt(self.rx[i])
+        return self.ref_rows
+
+    ref_sample = "4 rows of the 4096 per step: galois.ntt(x[i]) on GF(998244353) arrays (Numba fft_jit, _function.py:337-352)"
 
     def cpu_step(self, threads):
         import oracle
@@ -318,6 +401,7 @@ class RsDecode:
         self.rs = gb.ReedSolomon(255, 223)
         lo, hi = shard_bounds(total, rank, world)
         self.N = hi - lo
+        self.batch_total = total
         self.name = f"RS(255,223) decode, {total} codewords x 16 errors sharded over {world} GPU(s) (BASELINE configs[4])"
         GF = self.rs.field
         M = GF.Random((self.N, 223), seed=6 + rank)
@@ -346,18 +430,56 @@ class RsDecode:
     def step(self):
         self.dec, self.nerr = self.rs.decode_device(self.R, erasures=self.E)
 
+    def gather_tensor(self):
+        return self.dec.tensor.view(self.N, 255)
+
     def check(self):
         assert bool((self.nerr == self.n_err).all()), "not every codeword reported the injected number of errors"
         assert bool((self.dec.tensor.view(self.N, 255) == self.C).all()), "decoded codewords differ from the originals"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.hR = self.R.cpu()
         self.hE = self.E.cpu().numpy().astype(bool) if self.E is not None else None
         self.h2d, self.d2h = 255 * self.N * (2 if self.E is not None else 1), 255 * self.N + 8 * self.N
         self.e2e_units = self.N
+        self.e2e_api = "galois_b200.ReedSolomon(255,223).decode on pinned host ndarrays (gfb_rs_decode_host)"
+        if galois is not None and type(self) in (RsDecode, RsDecodeErasures):
+            self.rrs = galois.ReedSolomon(255, 223)
+            self.RGF = self.gb.enable(self.rrs.field)
+            self.hR = np.array(np.asarray(self.hR)).view(self.RGF)  # pageable copy owned by the reference class
+            self.e2e_api = ("galois.ReedSolomon(255,223).decode (the unmodified reference) after galois_b200.enable(rs.field), "
+                            "pageable host ndarrays -> bch_decode_jit hook -> gfb_rs_decode_host")
 
     def e2e_step(self):
-        self.hz = self.rs.decode(self.hR, erasures=self.hE, output="codeword", errors=True)
+        rs = getattr(self, "rrs", self.rs)
+        self.hz = rs.decode(self.hR, erasures=self.hE, output="codeword", errors=True)
+
+    def e2e_teardown(self):
+        if hasattr(self, "RGF"):
+            dec, nerr = self.hz
+            assert type(dec) is self.RGF and bool((nerr == self.n_err).all())
+            assert np.array_equal(np.asarray(dec), self.C.cpu().numpy()), "e2e decode differs from the original codewords"
+            self.gb.disable(self.RGF)
+
+    ref_cw = 200
+
+    def ref_setup(self, galois):
+        self.rrs = galois.ReedSolomon(255, 223)
+        GF = self.rrs.field
+        rng = np.random.default_rng(7)
+        C = self.rrs.encode(GF.Random((self.ref_cw, 223), seed=6))
+        E = np.zeros((self.ref_cw, 255), dtype=bool)
+        for i in range(self.ref_cw):
+            pos = rng.choice(255, self.n_err + self.n_era, replace=False)
+            C[i, pos] ^= GF(rng.integers(1, 256, pos.size, dtype=np.uint8))
+            E[i, pos[self.n_err:]] = True
+        self.rR, self.rE = C, (E if self.n_era else None)
+
+    def ref_step(self):
+        self.rz = self.rrs.decode(self.rR, erasures=self.rE, errors=True)
+        return self.ref_cw
+
+    ref_sample = "200 codewords per step: galois.ReedSolomon(255,223).decode(..., errors=True) (Numba bch_decode_jit, _bch.py:1337-1578)"
 
     def cpu_step(self, threads):
         import oracle
@@ -414,8 +536,23 @@ class Gf128Mul:
         got = self.out.tensor[: 16 * k].cpu().numpy().view(np.uint64).reshape(-1, 2)
         assert np.array_equal(got, O.mul(la, lb, threads=8)), "GPU GF(2^128) product differs from the oracle"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.e2e_units = None
+
+    ref_n = 20000
+
+    def ref_setup(self, galois):
+        GF = galois.GF(2**128, irreducible_poly="x^128 + x^7 + x^2 + x + 1", primitive_element=2, verify=False)
+        rng = np.random.default_rng(5)
+        limbs = rng.integers(0, 2**64, (2, self.ref_n, 2), dtype=np.uint64)
+        mk = lambda l: GF([int(lo) | (int(hi) << 64) for lo, hi in l])  # noqa: E731
+        self.rx, self.ry = mk(limbs[0]), mk(limbs[1])
+
+    def ref_step(self):
+        self.rz = self.rx * self.ry
+        return self.ref_n
+
+    ref_sample = "2e4 elements per step: x * y on galois.GF(2^128) object arrays (python-calculate, _calculate.py:309-324)"
 
     def cpu_step(self, threads):
         import oracle
@@ -507,7 +644,32 @@ class Ewise:
             else F.binary_op(opc[self.op], a, b, threads=8)
         assert np.array_equal(got, want), f"GPU {self.name} differs from the oracle"
 
-    def e2e_setup(self):
+    def ref_setup(self, galois):
+        GF = galois.GF(self.field_order, **self.field_kw)
+        n = self.ref_n if self.ref_n else min(self.n, 10**7)
+        if GF.dtypes == [np.object_]:
+            rng = np.random.default_rng(1)
+            mk = lambda: GF([int(lo) | (int(hi) << 64) | 1 for lo, hi in rng.integers(0, 2**63, (n, 2))])  # noqa: E731
+            self.rx, self.ry = mk(), mk()
+        else:
+            self.rx = GF.Random(n, seed=1, dtype=self.np_dtype)
+            self.ry = GF.Random(n, seed=2, low=1, dtype=self.np_dtype)
+        self.ref_count = n
+
+    def ref_step(self):
+        if self.op == "inv":
+            self.rz = np.reciprocal(self.ry)
+        elif self.op == "neg":
+            self.rz = -self.ry
+        else:
+            self.rz = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.true_divide}[self.op](self.rx, self.ry)
+        return self.ref_count
+
+    ref_n = 0
+    ref_sample = "min(n, 1e7)-element arrays through the reference's own ufunc on galois.GF arrays (single thread)"
+
+    def e2e_setup(self, galois=None):
+        self.e2e_api = "galois_b200 FieldArray ufunc on pinned host ndarrays (gfb_*_host)"
         if self.eb == 16:
             self.e2e_units = None  # object-dtype host arrays: conversion cost dominates, not a transfer benchmark
             return
@@ -571,7 +733,8 @@ EWISE = {
     "gf2_32_mul": _ewise("gf2_32_mul", op="mul", field_order=2**32, np_dtype=np.uint32, dtype="uint32", n=10**7,
                          kernel="k_binary<u32, BinaryCalc, MUL>", cpu_n=10**6),
     "gf2_128_inv": _ewise("gf2_128_inv", op="inv", field_order=2**128, field_kw=GCM, np_dtype=np.object_, dtype="u128",
-                          n=10**6, kernel="k_unary<u128, Binary128, INV>", cpu_n=200, cpu_per_thread=True, eb_cpu=16),
+                          n=10**6, kernel="k_unary<u128, Binary128, INV>", cpu_n=200, cpu_per_thread=True, eb_cpu=16,
+                          ref_n=100),
 }
 
 WORKLOADS = {"gfp_mul": GfpMul, "ntt": Ntt, "rs_decode": RsDecode, "gf2_128_mul": Gf128Mul}
@@ -613,7 +776,7 @@ class RsEncode(RsDecode):
         got = self.dC.tensor[: 255 * 2000].cpu().numpy().reshape(2000, 255)
         assert np.array_equal(got, ors.encode(np.asarray(self.M)[:2000], threads=8)), "GPU RS encode differs from the oracle"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.h2d, self.d2h, self.e2e_units = 223 * self.N, 255 * self.N, self.N
 
     def e2e_step(self):
@@ -698,6 +861,8 @@ class BchDecode(RsDecode):
     cpu_sample = "250 codewords per thread with 18 bit errors each (bch_decode_jit restatement, field GF(2), extension GF(2^8))"
 
 
+RsEncode.ref_setup = None  # no galois-driven leg for these two (oracle port only)
+BchDecode.ref_setup = None
 WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode, "intt": Intt, "bch_decode": BchDecode})
 
 
@@ -743,7 +908,7 @@ class MatInv:
         Ainv = R[:, n:].contiguous().cpu().numpy().astype(np.uint32).view(self.GF)
         assert np.array_equal(np.asarray(A @ Ainv), np.identity(n, dtype=np.uint32)), "A @ A^-1 != I"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.hA = self.GF.Random((self.n, self.n), seed=11)
         self.h2d = self.n * 2 * self.n * 4
         self.d2h = self.n * 2 * self.n * 4
@@ -809,7 +974,7 @@ class PolyRoots:
         assert np.all(np.diff(np.asarray(got).astype(np.int64)) > 0), "roots are not in increasing order"
         assert not np.asarray(self.gb.poly_evaluate(self.coeffs_host, got)).any(), "a reported root is not a root"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.poly = self.gb.Poly(self.coeffs_host)
         self.h2d = 4 * (self.degree + 1)
         self.d2h = 4 * self.degree
@@ -872,7 +1037,7 @@ class FftMixed:
         got = self.out.tensor[: 4 * self.N].view(self.torch.int32).cpu().numpy().astype(np.int64)
         assert np.array_equal(got, F.fft(row, omega)), "GPU mixed-radix DFT differs from the oracle"
 
-    def e2e_setup(self):
+    def e2e_setup(self, galois=None):
         self.e2e_rows = min(self.rows, 32)
         self.hx = self.GF.Random((self.e2e_rows, self.N), seed=31)
         self.h2d = self.d2h = 4 * self.N * self.e2e_rows
@@ -899,13 +1064,12 @@ WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMix
 
 
 def cpu_threads() -> int:
-    import oracle
+    """Threads of the oracle-port CPU figure: fixed by the machine, NOT by OMP_NUM_THREADS (torchrun sets that to 1)."""
+    return max(1, min(PORT_THREADS_CAP, os.cpu_count() or 1))
 
-    return max(1, min(oracle.max_threads(), os.cpu_count() or 1))
 
-
-def time_cpu(work, target_seconds=12.0, max_reps=50):
-    """Time `work.cpu_step` for roughly target_seconds; returns (units/s, reps, seconds, threads)."""
+def time_cpu(work, target_seconds=6.0, max_reps=50):
+    """Time `work.cpu_step` (oracle port, OpenMP) for roughly target_seconds; returns (units/s, reps, seconds, threads)."""
     threads = cpu_threads()
     work.cpu_step(threads)  # warm-up (allocations, page faults, OpenMP pool)
     units, reps, t0 = 0, 0, time.perf_counter()
@@ -918,14 +1082,26 @@ def time_cpu(work, target_seconds=12.0, max_reps=50):
     return units / dt, reps, dt, threads
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
-    Python + Numba and is not present on the GPU box), on every host thread it can use."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    cls = WORKLOADS[args.workload]
-    work = cls.__new__(cls)  # CPU leg only: no CUDA objects are created
+def has_ref(cls) -> bool:
+    return callable(getattr(cls, "ref_setup", None))
+
+
+def time_reference_live(work, galois, target_seconds=12.0, max_reps=30):
+    """Time the unmodified reference (`work.ref_step`) for roughly target_seconds -> (units/s, reps, seconds)."""
+    work.ref_setup(galois)
+    work.ref_step()  # JIT compilation + first-touch page faults
+    units, reps, t0 = 0, 0, time.perf_counter()
+    while reps < max_reps:
+        units += work.ref_step()
+        reps += 1
+        if time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return units / dt, reps, dt
+
+
+def port_setup(cls, work, threads):
+    """Inputs of the oracle-port leg when no CUDA object exists (the --impl reference process)."""
     if issubclass(cls, Ewise):
         import galois_b200 as gb
 
@@ -935,11 +1111,7 @@ def run_reference(args):
         import galois_b200 as gb
 
         work.GF = gb.GF(P_NTT)  # host-side constants only (omega)
-    threads = cpu_threads()
-    if cls is BchDecode:
-        pass  # builds its own received words in cpu_step
-    elif cls in (RsDecode, RsDecodeErasures):
-        # the CPU leg needs received words: build them with the oracle itself
+    if cls in (RsDecode, RsDecodeErasures):
         import oracle
 
         F = oracle.Field.binary(8, 0x11D, alpha=2)
@@ -954,27 +1126,101 @@ def run_reference(args):
             cE[i, pos[cls.n_err:]] = 1
         work.cR = C
         work.cE = cE if cls.n_era else None
+
+
+def workload_label(cls, work):
+    return getattr(work, "name", None) or getattr(cls, "name", None) or (cls.__doc__ or cls.__name__).strip().split("\n")[0].rstrip(".")
+
+
+def run_reference(args):
+    """--impl reference: the UNMODIFIED reference (baseline/_ref = `pip install --no-deps --target` of /root/reference)
+    through its own public API and stock code path — galois.GF arrays, Numba ufuncs / JIT functions, one thread (the
+    reference is single-threaded on this path) — on rank 0 only.  Each step is a bounded sample of the workload
+    (`cpu_baseline.sample`).  The OpenMP oracle port is printed next to it as `cpu_port` (fixed thread count).  If the
+    reference cannot be imported on this machine the port is the line's value and `cpu_baseline.kind` says "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cls = WORKLOADS[args.workload]
+    work = cls.__new__(cls)  # CPU legs only: no CUDA objects are created
+    threads = cpu_threads()
+    galois = load_reference() if has_ref(cls) else None
+    port = None
+    try:
+        port_setup(cls, work, threads)
+        pv, preps, psecs, pth = time_cpu(work, target_seconds=4.0 if galois is not None else 0.0)
+        port = {"value": pv, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", pth), "kind": "port",
+                "sample": f"{cls.cpu_sample}; {preps} repetitions in {psecs:.1f} s"}
+    except Exception as exc:  # the secondary figure must not take the line down
+        port = {"error": f"{type(exc).__name__}: {exc}"}
+
+    if galois is not None:
+        work.ref_setup(galois)
+        step, kind, cores, sample = work.ref_step, "reference", 1, cls.ref_sample
+        note = "the unmodified reference (baseline/_ref: galois + Numba) through its public API, single thread"
+    else:
+        step = lambda: work.cpu_step(threads)  # noqa: E731
+        kind, cores, sample = "port", getattr(cls, "cpu_cores", threads), cls.cpu_sample
+        note = "reference not importable here: CPU oracle port of the reference path (oracle/gf_oracle.c)"
     for _ in range(max(args.warmup, 1)):
-        work.cpu_step(threads)
+        step()
+    # bound the run: stop early (and say so) rather than exceed ~4 minutes
     t0 = time.perf_counter()
-    units = 0
+    units = done = 0
     for _ in range(args.steps):
-        units += work.cpu_step(threads)
+        units += step()
+        done += 1
+        if time.perf_counter() - t0 > 240.0:
+            break
     dt = time.perf_counter() - t0
     value = units / dt
     line = {
         "impl": "reference", "metric": cls.metric, "value": value, "unit": cls.unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
         "scaling": cls.scaling, "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
-        "config": {"workload": getattr(work, "name", None) or getattr(cls, "name", None) or (cls.__doc__ or cls.__name__).strip().split("\n")[0].rstrip("."),
-                   "note": "CPU oracle port of the reference path (oracle/gf_oracle.c); each step is a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", threads), "kind": "port",
-                         "sample": cls.cpu_sample},
+        "config": {"workload": workload_label(cls, work), "note": note},
+        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_port": port,
         "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if done != args.steps:
+        line["config"]["note"] += f"; stopped after {done} of {args.steps} steps (240 s bound)"
     print(json.dumps(line), flush=True)
     return 0
+
+
+def all_units(units: int, world: int) -> int:
+    if world == 1:
+        return units
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([units], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    return int(t.item())
+
+
+def time_gather(work, world):
+    """The path's only collective: the optional final all-gather of the row-sharded result."""
+    import torch
+
+    rows_total = getattr(work, "batch_total", None)
+    if world == 1 or rows_total is None or not hasattr(work, "gather_tensor"):
+        return None
+    from galois_b200._dist import gather_rows
+
+    flat = work.gather_tensor()
+    for _ in range(2):
+        gather_rows(flat, rows_total)
+    barrier_sync(world)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    full = gather_rows(flat, rows_total)
+    g1.record()
+    barrier_sync(world)
+    del full
+    return max_over_ranks(g0.elapsed_time(g1), world)
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -989,6 +1235,8 @@ def main():
     ap.add_argument("--gather", action="store_true", help="N>1: also time the final all-gather of the result shards")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads in the default run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-e2e", action="store_true", help="e2e through the galois_b200 mirror classes even if baseline/_ref exists")
+    ap.add_argument("--extras-ntt-batch", type=int, default=4096, help="total transforms of the secondary NTT workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -1009,7 +1257,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = time_steps(work.step, args.steps, args.warmup, world)
+    per_step = []
+    ms = time_steps(work.step, args.steps, args.warmup, world, per_step=per_step)
     clocks = sampler.stop() if rank == 0 else None
     work.check()
     workload_name = work.name
@@ -1017,55 +1266,75 @@ def main():
     per_gpu_units = work.units_per_step
 
     # whole-job units per step: per-rank shards may differ by one row when the batch does not divide evenly
-    units_all = work.units_per_step
-    if world > 1:
-        import torch.distributed as dist
-
-        t = torch.tensor([work.units_per_step], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        units_all = int(t.item())
+    units_all = all_units(work.units_per_step, world)
     total_units = units_all * args.steps
     value = total_units / (ms / 1e3)
 
     # optional: the final gather of the result shards (the only collective of the path), timed on its own
-    gather_ms = None
-    if args.gather and world > 1 and hasattr(work, "out"):
-        from galois_b200._dist import gather_rows
-
-        rows_total = getattr(work, "batch_total", None)
-        if rows_total is not None:
-            flat = work.out.tensor.view(work.rows, -1)
-            for _ in range(2):
-                gather_rows(flat, rows_total)
-            barrier_sync(world)
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            full = gather_rows(flat, rows_total)
-            g1.record()
-            barrier_sync(world)
-            gather_ms = max_over_ranks(g0.elapsed_time(g1), world)
-            del full
+    gather_ms = time_gather(work, world) if args.gather else None
     peak, peak_src = measured_hbm_peak()
     # dominant kernel: algorithmic bytes of one step on this rank / mean device time of one step
     achieved = work.units_per_step * cls.bytes_per_unit / (ms / 1e3 / args.steps) / 1e9
 
-    # ---- end to end through the public API with host buffers (same metric)
+    # ---- end to end through the reference-facing API with HOST buffers (same metric): the reference's own classes
+    #      with galois_b200.enable() when baseline/_ref is importable, else the mirror classes
+    galois = load_reference() if not args.no_ref_e2e else None
     e2e = None
-    work.e2e_setup()
+    work.e2e_setup(galois)
     if getattr(work, "e2e_units", work.units_per_step) is not None:
         e2e_units = getattr(work, "e2e_units", work.units_per_step)
         e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            work.e2e_step()
-        barrier_sync(world)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            work.e2e_step()
-        barrier_sync(world)
-        dt = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / 1e3
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            barrier_sync(world)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                fn()
+            barrier_sync(world)
+            return max_over_ranks((time.perf_counter() - t0) * 1e3, world) / 1e3
+
+        dt = timed(work.e2e_step)
         e2e = {"value": e2e_units * world * e2e_steps / dt, "unit": cls.unit, "h2d_bytes_per_step": work.h2d,
-               "d2h_bytes_per_step": work.d2h, "steps": e2e_steps,
-               "api": "FieldArray ufunc / ntt / ReedSolomon.decode on pinned host ndarrays (gfb_*_host pipeline)"}
+               "d2h_bytes_per_step": work.d2h, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": getattr(work, "e2e_api", "galois_b200 host API (gfb_*_host pipeline)")}
+        if hasattr(work, "e2e_pinned_step"):
+            dtp = timed(work.e2e_pinned_step)
+            e2e["pinned_value"] = e2e_units * world * e2e_steps / dtp
+            e2e["pinned_api"] = "galois_b200.GF mirror class, operands and result in pooled pinned memory"
+        if hasattr(work, "e2e_teardown"):
+            work.e2e_teardown()
+
+    # ---- secondary workloads (default run, EVERY N): the other BASELINE configs, device-resident, strong-scaled
+    #      over the ranks where the config shards (NTT batch 4096, RS 1e6 codewords), each with its own roofline
+    #      fraction and the time of the optional final gather
+    extras = {}
+    if args.workload == "gfp_mul" and not args.no_extras:
+        for name in ("x", "y", "out", "hx", "hy", "hz", "px", "py", "pz"):
+            if hasattr(work, name):
+                delattr(work, name)
+        torch.cuda.empty_cache()
+        for key, ecls, kw in (("ntt", Ntt, {"batch": args.extras_ntt_batch}), ("rs_decode", RsDecode, {"total": 10**6}),
+                              ("gf2_128_mul", Gf128Mul, {})):
+            try:
+                w = ecls(rank, world, **kw)
+                esteps = 5
+                ems = time_steps(w.step, esteps, 3, world)
+                w.check()
+                eunits = all_units(w.units_per_step, world)
+                ach = w.units_per_step * ecls.bytes_per_unit / (ems / esteps / 1e3) / 1e9
+                extras[key] = {"metric": ecls.metric, "value": eunits * esteps / (ems / 1e3), "unit": ecls.unit,
+                               "workload": w.name, "scaling": ecls.scaling, "ms_per_step": ems / esteps,
+                               "units_per_gpu_per_step": w.units_per_step,
+                               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                            "kernel": ecls.kernel, "algorithmic_bytes_per_unit": ecls.bytes_per_unit}}
+                if world > 1 and ecls.scaling == "strong":
+                    extras[key]["final_gather_ms"] = time_gather(w, world)
+                del w
+                torch.cuda.empty_cache()
+            except Exception as exc:  # a secondary workload must not take the headline down
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
@@ -1075,36 +1344,28 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- CPU baseline on the host cores (rank 0, N = 1 only), bounded sample
-    cpu = None
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only), bounded samples: the unmodified reference when it is
+    #      importable (single thread, as the reference runs), and the OpenMP oracle port as a second figure
+    cpu = port = None
     if world == 1 and not args.no_cpu:
-        v, reps, secs, threads = time_cpu(work)
-        cpu = {"value": v, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", threads), "kind": "port",
-               "sample": f"{cls.cpu_sample}; {reps} repetitions in {secs:.1f} s"}
+        try:
+            v, reps, secs, threads = time_cpu(work)
+            port = {"value": v, "unit": cls.unit, "cores": getattr(cls, "cpu_cores", threads), "kind": "port",
+                    "sample": f"{cls.cpu_sample}; {reps} repetitions in {secs:.1f} s"}
+        except Exception as exc:
+            port = {"error": f"{type(exc).__name__}: {exc}"}
+        if galois is not None and has_ref(cls):
+            v, reps, secs = time_reference_live(work, galois)
+            cpu = {"value": v, "unit": cls.unit, "cores": 1, "kind": "reference",
+                   "sample": f"{cls.ref_sample}; {reps} repetitions in {secs:.1f} s"}
+        else:
+            cpu = port
 
-    # ---- secondary workloads (default run only): short device-resident timings of the other BASELINE configs
-    extras = {}
-    if world == 1 and args.workload == "gfp_mul" and not args.no_extras:
-        del work
-        torch.cuda.empty_cache()
-        for key, ecls, kw in (("ntt", Ntt, {"batch": 512}), ("rs_decode", RsDecode, {"total": 10**6}),
-                              ("gf2_128_mul", Gf128Mul, {})):
-            try:
-                w = ecls(0, 1, **kw)
-                ems = time_steps(w.step, 5, 3, 1)
-                w.check()
-                extras[key] = {"metric": ecls.metric, "value": w.units_per_step * 5 / (ems / 1e3), "unit": ecls.unit,
-                               "workload": w.name, "ms_per_step": ems / 5,
-                               "hbm_gbs": w.units_per_step * ecls.bytes_per_unit / (ems / 5e3) / 1e9}
-                del w
-                torch.cuda.empty_cache()
-            except Exception as exc:  # a secondary workload must not take the headline down
-                extras[key] = {"error": f"{type(exc).__name__}: {exc}"}
-
+    med = statistics.median(per_step) if per_step else None
     line = {
         "metric": cls.metric, "value": value, "unit": cls.unit, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cls.scaling,
-        "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_median": med, "higher_is_better": True,
+        "scaling": cls.scaling, "vs_baseline": None, "dtype": cls.dtype, "data": "synthetic",
         "config": {"workload": workload_name, "parallelism": f"shard{world}",
                    "l2": "inputs larger than L2 (no flush needed)", "units_per_gpu_per_step": per_gpu_units},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -1114,6 +1375,10 @@ def main():
                      "algorithmic_bytes_per_step": cls.bytes_per_unit * per_gpu_units},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    if port is not None and port is not cpu:
+        line["cpu_port"] = port
+    if med is not None:
+        line["value_at_median"] = units_all / (med / 1e3)
     if gather_ms is not None:
         line["final_gather_ms"] = gather_ms
     if extras:

@@ -13,6 +13,7 @@ kernels (galois_b200/csrc).  There is no CPU fallback.
 """
 
 from ._field import GF, DeviceArray, Field, FieldArray
+from ._binding import disable, enable, is_enabled
 from ._lib import BackendUnavailable
 from ._linalg import poly_evaluate
 from ._poly import Poly, poly_roots
@@ -20,5 +21,5 @@ from ._ntt import intt, ntt, ntt_device
 from ._rs import BCH, ReedSolomon
 
 __all__ = ["GF", "Field", "FieldArray", "DeviceArray", "ntt", "intt", "ntt_device", "ReedSolomon", "BCH", "poly_evaluate", "poly_roots", "Poly",
-           "BackendUnavailable"]
+           "BackendUnavailable", "enable", "disable", "is_enabled"]
 __version__ = "0.1.0"

@@ -151,6 +151,34 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
             if self.dtype not in [np.dtype(d) for d in type(self).dtypes]:
                 raise TypeError(f"{type(self).name} can only have integer dtypes {[np.dtype(d).name for d in type(self).dtypes]}, not {self.dtype}.")
 
+    # getters / setters / casts (_domains/_array.py:413-451) --------------------------------------
+    def __getitem__(self, key):
+        """A single element comes back as a 0-d field array, not a bare NumPy integer, so arithmetic on it stays in
+        the field (_domains/_array.py:413-421)."""
+        item = super().__getitem__(key)
+        if np.isscalar(item):
+            item = type(self)(item, dtype=self.dtype)
+        return item
+
+    def __setitem__(self, key, value):
+        """Assigned values must be field elements: the kernels rely on 0 <= x < order (_domains/_array.py:423-429)."""
+        cls = type(self)
+        if isinstance(value, FieldArray):
+            if not isinstance(value, cls):
+                raise TypeError(f"{cls.name} arrays can only be assigned elements of {cls.name}, not {type(value)}.")
+        else:
+            value = cls._verify_array_like(value, self.dtype)
+        super().__setitem__(key, value)
+
+    def astype(self, dtype, order="K", casting="unsafe", subok=True, copy=True):
+        """Only the field's own integer dtypes are valid targets (_domains/_array.py:445-451)."""
+        cls = type(self)
+        if np.dtype(dtype) not in [np.dtype(d) for d in cls.dtypes]:
+            raise TypeError(
+                f"{cls.name} arrays can only be cast as integer dtypes in {[np.dtype(d).name for d in cls.dtypes]}, not {np.dtype(dtype).name}."
+            )
+        return super().astype(dtype, order=order, casting=casting, subok=subok, copy=copy)
+
     # alternate constructors (_domains/_array.py:188-320) ----------------------------------------
     @classmethod
     def Zeros(cls, shape, dtype=None):
@@ -501,8 +529,13 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
         """Bring an arbitrary Python-int exponent into int64 range without changing a**e (a != 0)."""
         if -(2**63) <= e < 2**63:
             return e
-        r = e % (cls.order - 1)
-        return r if r or e == 0 else cls.order - 1
+        q1 = cls.order - 1
+        if e < 0:
+            # keep the sign: 0 ** negative must still raise ZeroDivisionError in the kernel
+            r = (-e) % q1
+            return -(r if r else q1)
+        r = e % q1
+        return r if r else q1
 
     @classmethod
     def _reduce(cls, op, a, axis, keepdims, dtype):

@@ -47,6 +47,47 @@ static uint32_t host_mul_binary(uint32_t a, uint32_t b, int m, uint32_t poly) {
 
 }  // namespace gfb
 
+namespace gfb {
+// deterministic Miller-Rabin for n < 2^32 (bases 2, 7, 61)
+static uint32_t mulmod_u32(uint32_t a, uint32_t b, uint32_t n) { return (uint32_t)((uint64_t)a * b % n); }
+static uint32_t powmod_u32(uint32_t a, uint32_t e, uint32_t n) {
+    uint32_t r = 1;
+    while (e) {
+        if (e & 1) r = mulmod_u32(r, a, n);
+        a = mulmod_u32(a, a, n);
+        e >>= 1;
+    }
+    return r;
+}
+static bool is_prime_u32(uint32_t n) {
+    if (n < 2) return false;
+    for (uint32_t q : {2u, 3u, 5u, 7u, 11u, 13u, 17u, 19u, 23u, 29u, 31u, 37u, 61u}) {
+        if (n == q) return true;
+        if (n % q == 0) return false;
+    }
+    uint32_t d = n - 1;
+    int r = 0;
+    while ((d & 1) == 0) {
+        d >>= 1;
+        ++r;
+    }
+    for (uint32_t a : {2u, 7u, 61u}) {
+        uint32_t x = powmod_u32(a, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < r; ++i) {
+            x = mulmod_u32(x, x, n);
+            if (x == n - 1) {
+                comp = false;
+                break;
+            }
+        }
+        if (comp) return false;
+    }
+    return true;
+}
+}  // namespace gfb
+
 extern "C" {
 
 int gfb_device_count(void) {
@@ -89,6 +130,12 @@ gfb_status gfb_field_create(gfb_field** out, int kind, uint64_t order_lo, int de
         if (order_lo < 2 || order_lo >= (1ull << 32)) {
             free(f);
             return order_lo >= (1ull << 32) ? GFB_ERR_UNSUPPORTED : GFB_ERR_BAD_ARG;
+        }
+        if (!gfb::is_prime_u32((uint32_t)order_lo)) {
+            // even p > 2 has no p^-1 mod 2^32 and a composite p breaks Fermat inversion: refuse instead of
+            // returning garbage from mul / inv (the Python factory validates too, but this is the boundary)
+            free(f);
+            return GFB_ERR_BAD_ARG;
         }
         f->degree = 1;
         f->order_lo = order_lo;

@@ -69,6 +69,7 @@ static gfb_status ewise_host(gfb_field* f, int n_in, const void* const* in, cons
     if (!out) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
+    DrainOnExit drain_guard(hp);
     size_t widest = out_bytes;
     for (int i = 0; i < n_in; ++i) widest = in_bytes[i] > widest ? in_bytes[i] : widest;
     // chunk length: a multiple of 16 elements keeps every chunk start 16-byte aligned

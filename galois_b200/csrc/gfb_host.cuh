@@ -30,4 +30,16 @@ struct HostPipeline {
     cudaError_t drain();
 };
 
+// Any early return out of a pipeline loop (a failed copy or launch) must not leave earlier chunks' asynchronous copies
+// running against the caller's buffers: every `*_host` function holds one of these for its whole body.
+struct DrainOnExit {
+    HostPipeline* hp;
+    explicit DrainOnExit(HostPipeline* p) : hp(p) {}
+    ~DrainOnExit() {
+        if (hp) hp->drain();
+    }
+    DrainOnExit(const DrainOnExit&) = delete;
+    DrainOnExit& operator=(const DrainOnExit&) = delete;
+};
+
 }  // namespace gfb

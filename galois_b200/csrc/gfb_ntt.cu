@@ -642,14 +642,11 @@ template <typename T, bool LAZY, int LOG_RA>
 static gfb_status run_fast_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
     Mod<LAZY> md{pl->p, pl->p * 2u};
     const Radix32Roots rt = roots_of(pl);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kFastSmem));
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, false, LOG_RA + 5>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        attr_set = true;
-    }
+    // per-device attribute (several devices per process are supported): set on every call, it is cheap
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass1<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFastSmem));
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, false, LOG_RA + 5>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
     const int log_n1 = LOG_RA + 5;
     const size_t chunk = fast_chunk(pl);
     for (size_t off = 0; off < batch; off += chunk) {
@@ -670,12 +667,9 @@ template <typename T, bool LAZY, int LOG_N1>
 static gfb_status run_fast_short(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
     Mod<LAZY> md{pl->p, pl->p * 2u};
     const Radix32Roots rt = roots_of(pl);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, (LOG_N1 < 4), LOG_N1>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-        attr_set = true;
-    }
+    // per-device attribute (several devices per process are supported): set on every call, it is cheap
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass2<T, LAZY, (LOG_N1 < 4), LOG_N1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
     const size_t chunk = fast_chunk(pl);
     for (size_t off = 0; off < batch; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
@@ -701,12 +695,9 @@ template <typename T, bool LAZY, int LOG_RA>
 static gfb_status run_small_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, cudaStream_t st) {
     Mod<LAZY> md{pl->p, pl->p * 2u};
     const Radix32Roots rt = roots_of(pl);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_small<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kFastSmem));
-        attr_set = true;
-    }
+    // per-device attribute (several devices per process are supported): set on every call, it is cheap
+    GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_small<T, LAZY, LOG_RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFastSmem));
     const uint32_t scale_sh = (uint32_t)((((unsigned long long)pl->scale) << 32) / pl->p);
     k_ntt_small<T, LAZY, LOG_RA><<<(unsigned)((batch + kTileW - 1) / kTileW), kFastThreads, kFastSmem, st>>>(
         md, rt, pl->d_zt, x, y, batch, pl->scale, scale_sh);
@@ -1126,6 +1117,7 @@ gfb_status gfb_ntt_exec_host(gfb_ntt_plan* pl, int eb, const void* x, void* y, s
     if (!x || !y || (eb != 4 && eb != 8)) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
+    DrainOnExit drain_guard(hp);
     const size_t row_bytes = pl->n * (size_t)eb;
     size_t rows = kChunkBytes / row_bytes;
     if (rows == 0) rows = 1;

@@ -623,6 +623,7 @@ gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8
     if (ks < 1 || ks > rs->k) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
+    DrainOnExit drain_guard(hp);
     const size_t ns = (size_t)ks + (rs->n - rs->k);
     const size_t chunk = kChunkBytes / kMaxN;  // codewords per chunk
     gfb_status status = GFB_OK;
@@ -653,6 +654,7 @@ gfb_status gfb_rs_decode_host(gfb_rs_code* rs, const uint8_t* received, const ui
     if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
+    DrainOnExit drain_guard(hp);
     const size_t chunk = kChunkBytes / kMaxN;
     gfb_status status = GFB_OK;
     for (size_t c = 0, off = 0; off < N && status == GFB_OK; ++c, off += chunk) {

@@ -241,3 +241,48 @@ def test_fft_size_checks_need_no_gpu():
         np.fft.fft(gb.GF(2**8).Random(16, seed=1))
     with pytest.raises(NotImplementedError):
         np.fft.fft(gb.GF(2**100).Random(3, seed=1))
+
+
+def test_getitem_setitem_astype_stay_in_the_field():
+    """scalar indexing, assignment and casts follow _domains/_array.py:413-451 (no GPU needed)."""
+    import galois_b200 as gb
+
+    GF = gb.GF(7)
+    x = GF([1, 2, 3, 4])
+    assert type(x[0]) is GF and x[0].ndim == 0 and x[0].dtype == x.dtype
+    assert type(x[1:3]) is GF
+    x[0] = 6
+    x[1:3] = [0, 5]
+    x[3] = GF(2)
+    assert np.array_equal(np.asarray(x), [6, 0, 5, 2])
+    with pytest.raises(ValueError):
+        x[0] = 100
+    with pytest.raises(ValueError):
+        x[0:2] = [1, 7]
+    with pytest.raises(ValueError):
+        x[0] = -1
+    with pytest.raises(TypeError):
+        x[0] = 1.5
+    with pytest.raises(TypeError):
+        x[0] = gb.GF(5)(1)
+    assert np.array_equal(np.asarray(x), [6, 0, 5, 2])  # failed assignments left the array untouched
+    assert x.astype(np.int64).dtype == np.int64 and type(x.astype(np.int64)) is GF
+    with pytest.raises(TypeError):
+        x.astype(np.float64)
+    with pytest.raises(TypeError):
+        gb.GF(2**31 - 1)([1, 2]).astype(np.uint8)
+    W = gb.GF(2**100)
+    w = W([1 << 90, 5])
+    assert type(w[0]) is W and int(w[0]) == 1 << 90
+
+
+def test_reduce_exponent_keeps_the_sign():
+    """a huge negative exponent must stay negative so that 0 ** e still raises in the kernel."""
+    import galois_b200 as gb
+
+    GF = gb.GF(31)
+    assert GF._reduce_exponent(-(2**70)) < 0
+    assert GF._reduce_exponent(-(2**70)) % 30 == (-(2**70)) % 30
+    assert GF._reduce_exponent(2**70) % 30 == (2**70) % 30 and GF._reduce_exponent(2**70) > 0
+    assert GF._reduce_exponent(-30 * 2**70) == -30  # multiple of order - 1: a ** e = 1 for a != 0, still negative
+    assert GF._reduce_exponent(5) == 5
