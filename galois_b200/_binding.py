@@ -245,7 +245,10 @@ class CudaUFunc:
 
     # -- NumPy ufunc surface
     def __call__(self, *inputs, out=None, where=True, casting=None, dtype=None, order=None, subok=None, **_kw):
-        if self._small(inputs):
+        if self._small(inputs) or where is not True:
+            # where=: the reference's compiled ufuncs reject a mask ("... flagged as the ARRAYMASK ..." ValueError from
+            # NumPy's iterator) while its overrides / pure-Python ufuncs honour it; hand the call to the reference's own
+            # ufunc so every one of those behaviours is reproduced verbatim
             kw = {} if out is None else {"out": out}
             if where is not True:
                 kw["where"] = where
@@ -258,23 +261,16 @@ class CudaUFunc:
         wd = self._work_dtype(inputs)
         if self.kind == _UN:
             a = self._as_field_operand(inputs[0], wd)
-            if where is not True and self.op == _lib.GFB_INV:
-                a = np.where(np.broadcast_to(where, a.shape), a, 1)  # masked-out lanes are never inverted in NumPy
             res = M._unary(self.op, a, wd)
         elif self.kind == _POW:
             base = self._as_field_operand(inputs[0], wd)
             expo = inputs[1]
             if isinstance(expo, np.ndarray) and expo.ndim == 0:
                 expo = expo.item()
-            if where is not True:
-                shape = np.broadcast_shapes(np.shape(base), np.shape(expo))
-                expo = np.where(np.broadcast_to(where, shape), np.broadcast_to(expo, shape), 1)
             res = M._power([base.view(M), expo], [0, 1], wd)
         else:
             a = self._as_field_operand(inputs[0], wd)
             b = self._as_field_operand(inputs[1], wd)
-            # division under where=: the reference inverts the WHOLE denominator first (_ufunc.py:436), so a zero raises
-            # even where the mask is False; the fused kernel flags it the same way
             res = M._binary(self.op, a, b, wd)
         return self._finish(res, out, where, dtype)
 
@@ -618,7 +614,7 @@ def _install_hooks():
         div_orig = r_ufunc.divide_ufunc.__call__
 
         def divide_call(self, ufunc, method, inputs, kwargs, meta):
-            if _is_cuda(self.field) and method == "__call__" and not self.override:
+            if _is_cuda(self.field) and method == "__call__" and not self.override and kwargs.get("where", True) is True:
                 self._verify_operands_in_same_field(ufunc, inputs, meta)
                 inputs, kwargs = self._view_inputs_as_ndarray(inputs, kwargs)
                 output = self.ufunc(*inputs, **kwargs)
