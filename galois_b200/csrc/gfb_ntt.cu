@@ -297,6 +297,16 @@ struct Mod {
             a = s;
         }
     }
+    // unit-twiddle butterfly whose inputs are known to be below 2p (canonical loads, Shoup products): no reductions
+    __device__ __forceinline__ void bfly1_in2p(uint32_t& a, uint32_t& b) const {
+        if constexpr (LAZY) {
+            const uint32_t s = a + b;
+            b = a - b + p2;
+            a = s;
+        } else {
+            bfly1(a, b);
+        }
+    }
     // bring a lazy value into [0, p)
     __device__ __forceinline__ uint32_t canon(uint32_t x) const {
         if constexpr (LAZY) x = csub(x, p2);
@@ -315,7 +325,7 @@ __host__ __device__ constexpr int brev(int i) {
 }
 __host__ __device__ constexpr int brev5(int i) { return brev<5>(i); }
 
-template <bool LAZY, int LOG_R, int S>
+template <bool LAZY, int LOG_R, int S, bool IN2P = false>
 __device__ __forceinline__ void radix_stage(uint32_t (&v)[1 << LOG_R], const Mod<LAZY>& md, const Radix32Roots& rt) {
     constexpr int half = 1 << S;
 #pragma unroll
@@ -323,16 +333,21 @@ __device__ __forceinline__ void radix_stage(uint32_t (&v)[1 << LOG_R], const Mod
         const int j = g & (half - 1);
         const int k = (g >> S) << (S + 1);
         const int e = j * (16 >> S);
-        if (e == 0)
-            md.bfly1(v[k + j], v[k + j + half]);
-        else
+        if (e == 0) {
+            if constexpr (IN2P)
+                md.bfly1_in2p(v[k + j], v[k + j + half]);
+            else
+                md.bfly1(v[k + j], v[k + j + half]);
+        } else {
             md.bfly(v[k + j], v[k + j + half], rt.w[e], rt.ws[e]);
+        }
     }
 }
 
-template <bool LAZY, int LOG_R>
+// IN2P: every input is below 2p (stage 0 then needs no conditional subtractions in the lazy representation)
+template <bool LAZY, int LOG_R, bool IN2P = false>
 __device__ __forceinline__ void radixR(uint32_t (&v)[1 << LOG_R], const Mod<LAZY>& md, const Radix32Roots& rt) {
-    if constexpr (LOG_R > 0) radix_stage<LAZY, LOG_R, 0>(v, md, rt);
+    if constexpr (LOG_R > 0) radix_stage<LAZY, LOG_R, 0, IN2P>(v, md, rt);
     if constexpr (LOG_R > 1) radix_stage<LAZY, LOG_R, 1>(v, md, rt);
     if constexpr (LOG_R > 2) radix_stage<LAZY, LOG_R, 2>(v, md, rt);
     if constexpr (LOG_R > 3) radix_stage<LAZY, LOG_R, 3>(v, md, rt);
@@ -617,6 +632,8 @@ __global__ void __launch_bounds__(kFastThreads, 2)
     }
 }
 
+#include "gfb_ntt_fused.cuh"
+
 // transforms per pass-1 / pass-2 launch pair: 74 * 2^20 elements of uint32 workspace; at N = 2^20 that is
 // 74 * 64 CTAs = 16 full waves of 2 CTAs/SM x 148 SMs
 // Tuning knob (experiments only): GFB_NTT_CHUNK=<transforms of 2^20> overrides the chunk, e.g. 18 keeps the 72 MiB
@@ -705,8 +722,43 @@ static gfb_status run_small_ra(gfb_ntt_plan* pl, const T* x, T* y, size_t batch,
     return GFB_OK;
 }
 
+// N = 2^20, uint32 elements: the persistent fused kernel (gfb_ntt_fused.cuh).  GFB_NTT_FUSED=0 selects the two-launch
+// kernels above instead (A/B measurements).
+static bool fused_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_NTT_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <bool LAZY>
+static gfb_status run_fused(gfb_ntt_plan* pl, const uint32_t* x, uint32_t* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    using namespace fused;
+    Mod<LAZY> md{pl->p, pl->p * 2u};
+    const Radix32Roots rt = roots_of(pl);
+    const size_t kMaxBatch = (size_t)1 << 24;  // tickets are 32-bit: 128 per transform
+    for (size_t off = 0; off < batch; off += kMaxBatch) {
+        const size_t cnt = batch - off < kMaxBatch ? batch - off : kMaxBatch;
+        const unsigned ring = (unsigned)(cnt < kRing ? cnt : kRing);
+        Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + ((size_t)ring << 20));
+        GFB_CUDA_TRY(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl) + 2 * cnt * sizeof(unsigned int), st));
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_fused<LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        size_t grid = (size_t)sm_count();
+        if (grid > cnt * 2 * kTilesPerPass) grid = cnt * 2 * kTilesPerPass;
+        k_ntt_fused<LAZY><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(md, rt, pl->d_zt, pl->d_tw4, x + (off << 20),
+                                                                          y + (off << 20), ws, ctrl, (unsigned)cnt, ring);
+        GFB_CUDA_TRY(cudaGetLastError());
+    }
+    return GFB_OK;
+}
+
 template <typename T, bool LAZY>
 static gfb_status run_fast_t(gfb_ntt_plan* pl, const T* x, T* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (pl->log_n == 20 && fused_enabled() && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)ws) & 15) == 0)
+            return run_fused<LAZY>(pl, (const uint32_t*)x, (uint32_t*)y, batch, ws, st);
+    }
     switch (pl->log_n) {
         case 5: return run_small_ra<T, LAZY, 0>(pl, x, y, batch, st);
         case 6: return run_small_ra<T, LAZY, 1>(pl, x, y, batch, st);
@@ -1074,7 +1126,12 @@ size_t gfb_ntt_workspace_bytes(const gfb_ntt_plan* pl, int elem_bytes, size_t ba
         if (pl->log_n <= 10) return 0;  // single kernel
         const size_t chunk = fast_chunk(pl);
         const size_t rows = batch < chunk ? batch : chunk;
-        return rows * pl->n * sizeof(uint32_t);
+        size_t bytes = rows * pl->n * sizeof(uint32_t);
+        if (pl->log_n == 20 && elem_bytes == 4) {  // the fused kernel: intermediate ring + task counters
+            const size_t fb = fused::workspace_bytes(batch);
+            if (fb > bytes) bytes = fb;
+        }
+        return bytes;
     }
     if (pl->n <= 2) return 0;
     size_t rows = kGenericWsBytes / (pl->n * sizeof(uint32_t));
@@ -1117,12 +1174,13 @@ gfb_status gfb_ntt_exec_host(gfb_ntt_plan* pl, int eb, const void* x, void* y, s
     if (!x || !y || (eb != 4 && eb != 8)) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
-    DrainOnExit drain_guard(hp);
+    PipelineScope scope(hp);
     const size_t row_bytes = pl->n * (size_t)eb;
     size_t rows = kChunkBytes / row_bytes;
     if (rows == 0) rows = 1;
     if (rows > batch) rows = batch;
     const size_t ws_bytes = gfb_ntt_workspace_bytes(pl, eb, rows);
+    const bool x_pinned = is_pinned_host(x), y_pinned = is_pinned_host(y);
     gfb_status status = GFB_OK;
     for (size_t c = 0, off = 0; off < batch && status == GFB_OK; ++c, off += rows) {
         const int slot = (int)(c % kSlots);
@@ -1132,10 +1190,11 @@ gfb_status gfb_ntt_exec_host(gfb_ntt_plan* pl, int eb, const void* x, void* y, s
         void* dy = hp->buffer(slot, 1, rows * row_bytes);
         void* dw = ws_bytes ? hp->buffer(slot, 2, ws_bytes) : nullptr;
         if (!dx || !dy || (ws_bytes && !dw)) return GFB_ERR_CUDA;
-        GFB_CUDA_TRY(cudaMemcpyAsync(dx, (const char*)x + off * row_bytes, cnt * row_bytes, cudaMemcpyHostToDevice, st));
+        GFB_CUDA_TRY(hp->begin_chunk(slot));
+        GFB_CUDA_TRY(hp->copy_in(slot, 0, dx, (const char*)x + off * row_bytes, cnt * row_bytes, x_pinned));
         status = gfb_ntt_exec(pl, eb, dx, dy, cnt, dw, st);
         if (status != GFB_OK) break;
-        GFB_CUDA_TRY(cudaMemcpyAsync((char*)y + off * row_bytes, dy, cnt * row_bytes, cudaMemcpyDeviceToHost, st));
+        GFB_CUDA_TRY(hp->copy_out(slot, 1, (char*)y + off * row_bytes, dy, cnt * row_bytes, y_pinned));
     }
     cudaError_t e = hp->drain();
     if (e != cudaSuccess) {

@@ -623,9 +623,10 @@ gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8
     if (ks < 1 || ks > rs->k) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
-    DrainOnExit drain_guard(hp);
+    PipelineScope scope(hp);
     const size_t ns = (size_t)ks + (rs->n - rs->k);
     const size_t chunk = kChunkBytes / kMaxN;  // codewords per chunk
+    const bool msg_pinned = is_pinned_host(msg), cw_pinned = is_pinned_host(cw);
     gfb_status status = GFB_OK;
     for (size_t c = 0, off = 0; off < N && status == GFB_OK; ++c, off += chunk) {
         const int slot = (int)(c % kSlots);
@@ -634,10 +635,11 @@ gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8
         uint8_t* dm = (uint8_t*)hp->buffer(slot, 0, chunk * kMaxN);
         uint8_t* dc = (uint8_t*)hp->buffer(slot, 1, chunk * kMaxN);
         if (!dm || !dc) return GFB_ERR_CUDA;
-        GFB_CUDA_TRY(cudaMemcpyAsync(dm, msg + off * ks, cnt * ks, cudaMemcpyHostToDevice, st));
+        GFB_CUDA_TRY(hp->begin_chunk(slot));
+        GFB_CUDA_TRY(hp->copy_in(slot, 0, dm, msg + off * ks, cnt * ks, msg_pinned));
         status = gfb_rs_encode(rs, dm, ks, dc, cnt, st);
         if (status != GFB_OK) break;
-        GFB_CUDA_TRY(cudaMemcpyAsync(cw + off * ns, dc, cnt * ns, cudaMemcpyDeviceToHost, st));
+        GFB_CUDA_TRY(hp->copy_out(slot, 1, cw + off * ns, dc, cnt * ns, cw_pinned));
     }
     cudaError_t e = hp->drain();
     if (e != cudaSuccess) {
@@ -654,8 +656,10 @@ gfb_status gfb_rs_decode_host(gfb_rs_code* rs, const uint8_t* received, const ui
     if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
     HostPipeline* hp = HostPipeline::get();
     if (!hp) return GFB_ERR_CUDA;
-    DrainOnExit drain_guard(hp);
+    PipelineScope scope(hp);
     const size_t chunk = kChunkBytes / kMaxN;
+    const bool rec_pinned = is_pinned_host(received), era_pinned = erasures && is_pinned_host(erasures);
+    const bool dec_pinned = is_pinned_host(decoded), nerr_pinned = is_pinned_host(n_errors);
     gfb_status status = GFB_OK;
     for (size_t c = 0, off = 0; off < N && status == GFB_OK; ++c, off += chunk) {
         const int slot = (int)(c % kSlots);
@@ -666,12 +670,13 @@ gfb_status gfb_rs_decode_host(gfb_rs_code* rs, const uint8_t* received, const ui
         uint8_t* dd = (uint8_t*)hp->buffer(slot, 2, chunk * kMaxN);
         int64_t* dn = (int64_t*)hp->buffer(slot, 3, chunk * sizeof(int64_t));
         if (!dr || !de || !dd || !dn) return GFB_ERR_CUDA;
-        GFB_CUDA_TRY(cudaMemcpyAsync(dr, received + off * ns, cnt * ns, cudaMemcpyHostToDevice, st));
-        if (erasures) GFB_CUDA_TRY(cudaMemcpyAsync(de, erasures + off * ns, cnt * ns, cudaMemcpyHostToDevice, st));
+        GFB_CUDA_TRY(hp->begin_chunk(slot));
+        GFB_CUDA_TRY(hp->copy_in(slot, 0, dr, received + off * ns, cnt * ns, rec_pinned));
+        if (erasures) GFB_CUDA_TRY(hp->copy_in(slot, 1, de, erasures + off * ns, cnt * ns, era_pinned));
         status = gfb_rs_decode(rs, dr, erasures ? de : nullptr, ns, dd, dn, cnt, st);
         if (status != GFB_OK) break;
-        GFB_CUDA_TRY(cudaMemcpyAsync(decoded + off * ns, dd, cnt * ns, cudaMemcpyDeviceToHost, st));
-        GFB_CUDA_TRY(cudaMemcpyAsync(n_errors + off, dn, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        GFB_CUDA_TRY(hp->copy_out(slot, 2, decoded + off * ns, dd, cnt * ns, dec_pinned));
+        GFB_CUDA_TRY(hp->copy_out(slot, 3, n_errors + off, dn, cnt * sizeof(int64_t), nerr_pinned));
     }
     cudaError_t e = hp->drain();
     if (e != cudaSuccess) {
