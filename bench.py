@@ -1060,7 +1060,176 @@ class FftMixed:
     cpu_sample = "max(threads, 8) transforms (one fft_jit-style mixed-radix transform per row, rows over OpenMP threads)"
 
 
-WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMixed})
+class Convolve:
+    """np.convolve of two 4096-coefficient polynomials over GF(998244353) (reference: 41 ms,
+    schoolbook because np.convolve would overflow, _function.py:147-149).  Here: three 8192-point NTTs."""
+
+    metric, unit, dtype, scaling = "gfp_convolve_4096x4096_per_sec", "convolution/s", "uint32", "weak"
+    kernel = "k_conv_pad -> k_ntt_small/four-step (x2 batched, x1) -> k_binary MUL -> k_conv_unpad"
+    na = nb = 4096
+    field_order = P_NTT
+    bytes_per_unit = 4 * (4096 + 4096 + 8191)  # compulsory: read a and b, write the 8191 coefficients
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200 import _lib
+
+        self.gb, self.torch, self._lib = gb, torch, _lib
+        self.GF = gb.GF(self.field_order)
+        self.np_dtype = self.GF.dtypes[0]
+        self.eb = np.dtype(self.np_dtype).itemsize
+        self.name = f"np.convolve, {self.na} x {self.nb} coefficients over {self.GF.name}, one pair per GPU per step"
+        self.ha = self.GF.Random(self.na, seed=41 + rank)
+        self.hb = self.GF.Random(self.nb, seed=42 + rank)
+        self.a, self.b = self.ha.to_device(), self.hb.to_device()
+        self.out = gb.DeviceArray.empty(self.GF, (self.na + self.nb - 1,), self.np_dtype)
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = 1, 6, 0, 0
+
+    def step(self):
+        st = self._lib.lib().gfb_convolve(self.GF._handle(), self.eb, self.a.data_ptr, self.na, self.b.data_ptr, self.nb,
+                                          self.out.data_ptr, self.gb.DeviceArray._stream())
+        self._lib.check(st, "gfb_convolve")
+
+    def _oracle(self):
+        import oracle
+
+        if self.GF._is_prime_field:
+            return oracle.Field.prime(self.GF.order)
+        return oracle.Field.binary(self.GF.degree, int(self.GF.irreducible_poly), alpha=int(self.GF.primitive_element))
+
+    def check(self):
+        want = self._oracle().convolve(np.asarray(self.ha).astype(np.int64), np.asarray(self.hb).astype(np.int64))
+        assert np.array_equal(np.asarray(self.out.cpu()).astype(np.int64), want), "GPU convolution differs from the oracle"
+
+    def e2e_setup(self, galois=None):
+        self.h2d, self.d2h = self.eb * (self.na + self.nb), self.eb * (self.na + self.nb - 1)
+        self.e2e_units = 1
+        self.e2e_api = "np.convolve on galois_b200 FieldArrays (gfb_convolve_host)"
+        if galois is not None:
+            self.RGF = self.gb.enable(galois.GF(self.field_order))
+            self.ha = self.RGF(np.asarray(self.ha))
+            self.hb = self.RGF(np.asarray(self.hb))
+            self.e2e_api = "np.convolve on the reference's galois.GF arrays after galois_b200.enable(GF) (convolve_jit hook -> gfb_convolve_host)"
+
+    def e2e_step(self):
+        self.hz = np.convolve(self.ha, self.hb)
+
+    def e2e_teardown(self):
+        if hasattr(self, "RGF"):
+            self.gb.disable(self.RGF)
+
+    def ref_setup(self, galois):
+        GF = galois.GF(self.field_order)
+        self.ra, self.rb = GF(np.asarray(self.ha)), GF(np.asarray(self.hb))
+
+    def ref_step(self):
+        self.rz = np.convolve(self.ra, self.rb)
+        return 1
+
+    ref_sample = "the same 4096 x 4096 np.convolve on galois.GF arrays (Numba convolve_jit, _function.py:111-167)"
+
+    def cpu_step(self, threads):
+        if not hasattr(self, "ca"):
+            self.ca = np.asarray(self.ha).astype(np.int64)
+            self.cb = np.asarray(self.hb).astype(np.int64)
+        self._oracle().convolve(self.ca, self.cb)
+        return 1
+
+    cpu_sample = "the same 4096 x 4096 convolution, schoolbook, one thread (convolve_jit's fall-back loop)"
+    cpu_cores = 1
+
+
+class ConvolveGf256(Convolve):
+    """np.convolve 4096 x 4096 over GF(2^8) (reference: 36 ms): schoolbook kernel, EXP/LOG tables in shared memory."""
+
+    metric = "gf256_convolve_4096x4096_per_sec"
+    kernel = "k_convolve<u8, BinaryLut>"
+    field_order = 2**8
+    dtype = "u8"
+    bytes_per_unit = 4096 + 4096 + 8191
+
+
+class MatmulRs:
+    """the RS(255,223) encode-shaped product (1e6 x 223) @ (223 x 32) over GF(2^8) through np.matmul's
+    kernel (the reference: single-threaded triple loop, 1.74e4 rows/s)."""
+
+    metric, unit, dtype, scaling = "gf256_matmul_rows_per_sec", "row/s", "u8", "weak"
+    kernel = "k_matmul<u8, BinaryLut>"
+    M, K, N = 10**6, 223, 32
+    bytes_per_unit = 223 + 32  # per row of A: read the row, write the 32 products (B is 7 KB, read once)
+
+    def __init__(self, rank, world):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200 import _lib
+
+        self.gb, self.torch, self._lib = gb, torch, _lib
+        self.GF = gb.GF(2**8)
+        self.name = f"({self.M} x {self.K}) @ ({self.K} x {self.N}) over GF(2^8), one product per GPU per step"
+        g = torch.Generator(device="cuda").manual_seed(51 + rank)
+        A = torch.randint(0, 256, (self.M, self.K), dtype=torch.uint8, device="cuda", generator=g)
+        B = torch.randint(0, 256, (self.K, self.N), dtype=torch.uint8, device="cuda", generator=g)
+        self.A = gb.DeviceArray(self.GF, A.reshape(-1), (self.M, self.K), np.uint8)
+        self.B = gb.DeviceArray(self.GF, B.reshape(-1), (self.K, self.N), np.uint8)
+        self.C = gb.DeviceArray.empty(self.GF, (self.M, self.N), np.uint8)
+        self.units_per_step, self.launches_per_step, self.h2d, self.d2h = self.M, 1, 0, 0
+
+    def step(self):
+        st = self._lib.lib().gfb_matmul(self.GF._handle(), 1, self.A.data_ptr, self.B.data_ptr, self.C.data_ptr, 1, self.M,
+                                        self.K, self.N, 0, self.gb.DeviceArray._stream())
+        self._lib.check(st, "gfb_matmul")
+
+    def check(self):
+        import oracle
+
+        F = oracle.Field.binary(8, int(self.GF.irreducible_poly), alpha=int(self.GF.primitive_element))
+        k = 2000
+        A = self.A.tensor.view(self.M, self.K)[:k].cpu().numpy().astype(np.int64)
+        B = self.B.tensor.view(self.K, self.N).cpu().numpy().astype(np.int64)
+        got = self.C.tensor.view(self.M, self.N)[:k].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, F.matmul(A, B, threads=8)), "GPU matmul differs from the oracle"
+
+    def e2e_setup(self, galois=None):
+        self.hA = self.A.cpu()
+        self.hB = self.B.cpu()
+        self.h2d, self.d2h, self.e2e_units = self.M * self.K + self.K * self.N, self.M * self.N, self.M
+        self.e2e_api = "A @ B on galois_b200 FieldArrays (gfb_matmul_host)"
+
+    def e2e_step(self):
+        self.hz = self.hA @ self.hB
+
+    ref_rows = 2000
+
+    def ref_setup(self, galois):
+        GF = galois.GF(2**8)
+        self.rA = GF.Random((self.ref_rows, self.K), seed=51)
+        self.rB = GF.Random((self.K, self.N), seed=52)
+
+    def ref_step(self):
+        self.rz = self.rA @ self.rB
+        return self.ref_rows
+
+    ref_sample = "2000 rows per step: A @ B on galois.GF(2^8) arrays (Numba matmul_jit, _linalg.py:286-308)"
+
+    def cpu_step(self, threads):
+        import oracle
+
+        if not hasattr(self, "cA"):
+            self.cF = oracle.Field.binary(8, 0x11D, alpha=2)
+            rng = np.random.default_rng(51)
+            self.cA = rng.integers(0, 256, (2000 * threads, self.K), dtype=np.int64)
+            self.cB = rng.integers(0, 256, (self.K, self.N), dtype=np.int64)
+        self.cF.matmul(self.cA, self.cB, threads=threads)
+        return len(self.cA)
+
+    cpu_sample = "2000 rows per thread (matmul_jit's triple loop with EXP/LOG lookups), rows over OpenMP threads"
+
+
+WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMixed, "convolve": Convolve,
+                  "convolve_gf256": ConvolveGf256, "matmul_rs": MatmulRs})
 
 
 def cpu_threads() -> int:

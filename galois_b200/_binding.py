@@ -319,7 +319,13 @@ class CudaUFunc:
         if self._small((a,)) or not hasattr(M, "_at"):
             args = (a, indices) if b is None else (a, indices, b)
             return self._reference().at(*args)
-        M._at(self.kind, self.op, a, indices, b)
+        wd = self._work_dtype((a,))
+        if not (isinstance(a, np.ndarray) and a.dtype == wd):
+            args = (a, indices) if b is None else (a, indices, b)
+            return self._reference().at(*args)
+        if b is not None and self.kind == _BIN:
+            b = self._as_field_operand(b, wd).view(M)
+        M._at(self.kind, self.op, a.view(M), indices, b)
         return None
 
 

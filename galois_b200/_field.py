@@ -350,14 +350,16 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
         kwargs.pop("where", None)
 
         if ufunc in _OPS_UNARY:
+            if method == "at":
+                return cls._at("unary", _OPS_UNARY[ufunc], inputs[0], inputs[1], None)
             if method != "__call__":
                 raise ValueError(f"Ufunc method {method!r} is not supported on {ufunc.__name__!r}. Reduction methods are only supported on binary functions.")
             result = cls._unary(_OPS_UNARY[ufunc], inputs[0], dtype)
         elif ufunc is np.power:
             if method in ("reduce", "accumulate", "reduceat"):
                 raise ValueError(f"Ufunc method {method!r} is not supported on 'power' because it takes inputs with type {cls.name} array and integer array.")
-            if method != "__call__" and method != "outer":
-                raise NotImplementedError(f"Ufunc method {method!r} of 'power' is not supported by the CUDA backend.")
+            if method == "at":
+                return cls._at("power", None, inputs[0], inputs[1], inputs[2])
             result = cls._power(inputs, operands, dtype, outer=(method == "outer"))
         elif ufunc in (np.divmod, np.remainder):
             if non_field:
@@ -401,8 +403,14 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
                 result = cls._binary(op, a2.view(cls), b.view(cls), dtype)
             elif method == "reduce":
                 result = cls._reduce(op, inputs[0], kwargs.get("axis", 0), kwargs.get("keepdims", False), dtype)
+            elif method == "accumulate":
+                result = cls._accumulate(op, inputs[0], kwargs.get("axis", 0), dtype)
+            elif method == "reduceat":
+                result = cls._reduceat(op, inputs[0], inputs[1], kwargs.get("axis", 0), dtype)
+            elif method == "at":
+                return cls._at("binary", op, inputs[0], inputs[1], inputs[2] if len(inputs) > 2 else None)
             else:
-                raise NotImplementedError(f"Ufunc method {method!r} is not supported by the CUDA backend (only __call__, outer, reduce).")
+                raise ValueError(f"Unknown ufunc method {method!r}.")
 
         if out is not None:
             target = out[0] if isinstance(out, tuple) else out
@@ -537,28 +545,67 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
         r = e % q1
         return r if r else q1
 
+    # -- ufunc methods (reduce / accumulate / reduceat / at): _domains/_ufunc.py:349,403 forwards them to the DUFunc;
+    #    here they are gfb_fold / gfb_fold_segments (csrc/gfb_fold.cu) plus the element-wise kernels
+    @classmethod
+    def _fold(cls, inner_op, x, axis, scan, dtype):
+        """Fold (scan=False) or running fold (scan=True) of ndarray ``x`` along ``axis`` with ADD or MUL."""
+        lib = _lib.lib()
+        x = np.ascontiguousarray(cls._prep(x, dtype))
+        axis = axis % x.ndim
+        moved = False
+        outer = int(np.prod(x.shape[:axis])) if axis else 1
+        length = x.shape[axis]
+        inner = int(np.prod(x.shape[axis + 1:])) if axis + 1 < x.ndim else 1
+        if inner != 1 and outer * inner < 2048 and length >= 8192:
+            # few long strided lines: make them contiguous so the chunked kernels apply
+            x = np.ascontiguousarray(np.moveaxis(x, axis, -1))
+            moved, outer, inner = True, outer * inner, 1
+        out_shape = x.shape if scan else (x.shape[:-1] if moved else x.shape[:axis] + x.shape[axis + 1:])
+        out = _pinned.empty(out_shape, dtype)
+        if out.size:
+            st = lib.gfb_fold_host(cls._handle(), inner_op, 1 if scan else 0, cls._elem_bytes(dtype), x.ctypes.data,
+                                   out.ctypes.data, outer, length, inner)
+            _lib.check(st, "gfb_fold_host")
+        if moved and scan:
+            out = np.moveaxis(out, -1, axis)
+        return out
+
     @classmethod
     def _reduce(cls, op, a, axis, keepdims, dtype):
-        """np.add.reduce / np.multiply.reduce (and the left folds of subtract / divide) as a pairwise tree of
-        element-wise kernels."""
+        """np.add.reduce / np.multiply.reduce, and the left folds of subtract / divide (a0 - a1 - ... = a0 - sum(rest))."""
         x = np.asarray(a.view(np.ndarray))
         if axis is None:
             x = x.reshape(-1)
             axis = 0
-        x = np.moveaxis(x, axis, 0)
-        if x.shape[0] == 0:
+        if isinstance(axis, tuple):
+            res = x.view(cls)
+            for ax in sorted((v % x.ndim for v in axis), reverse=True):
+                res = cls._reduce(op, np.atleast_1d(res).view(cls), ax, keepdims, dtype)
+            return res
+        axis = axis % max(x.ndim, 1)
+        if x.shape[axis] == 0:
             raise ValueError("zero-size array to reduction operation which has no identity")
-        if op in (_lib.GFB_SUB, _lib.GFB_DIV) and x.shape[0] > 1:
-            inner = _lib.GFB_ADD if op == _lib.GFB_SUB else _lib.GFB_MUL
-            rest = cls._tree(inner, x[1:], dtype)
-            res = cls._binary(op, x[0].view(cls), rest, dtype)
+        inner_op = _lib.GFB_ADD if op in (_lib.GFB_ADD, _lib.GFB_SUB) else _lib.GFB_MUL
+        if cls._wide:
+            xm = np.moveaxis(x, axis, 0)
+            if op in (_lib.GFB_SUB, _lib.GFB_DIV) and xm.shape[0] > 1:
+                res = cls._binary(op, xm[0].view(cls), cls._tree(inner_op, xm[1:], dtype), dtype)
+            else:
+                res = cls._tree(inner_op, xm, dtype)
+            res = np.asarray(res)
+        elif op in (_lib.GFB_SUB, _lib.GFB_DIV) and x.shape[axis] > 1:
+            head = np.take(x, 0, axis=axis)
+            rest = cls._fold(inner_op, x[(slice(None),) * axis + (slice(1, None),)], axis, False, dtype)
+            res = np.asarray(cls._binary(op, np.asarray(head).view(cls), np.asarray(rest).view(cls), dtype))
         else:
-            res = cls._tree(op if op in (_lib.GFB_ADD, _lib.GFB_MUL) else _lib.GFB_ADD, x, dtype)
+            res = cls._fold(inner_op, x, axis, False, dtype)
         if keepdims:
             res = np.expand_dims(res, axis)
+        res = np.asarray(res)
         if res.ndim == 0:
-            return cls(res.item() if not cls._wide else int(res.item()), dtype=dtype)
-        return res
+            return cls(int(res.item()), dtype=dtype)
+        return res.view(cls)
 
     @classmethod
     def _tree(cls, op, x, dtype):
@@ -571,6 +618,121 @@ class FieldArray(np.ndarray, metaclass=FieldMeta):
                 head = np.concatenate([head, cur[2 * half:]], axis=0)
             cur = head
         return cur[0].view(cls) if isinstance(cur[0], np.ndarray) else cls(cur[0], dtype=dtype)
+
+    @classmethod
+    def _accumulate(cls, op, a, axis, dtype):
+        """np.<ufunc>.accumulate: out[k] = a0 (op) a1 (op) ... (op) ak along ``axis``."""
+        if cls._wide:
+            raise NotImplementedError(f"ufunc.accumulate is not implemented over {cls.name} (elements wider than 64 bits).")
+        x = np.asarray(a.view(np.ndarray))
+        if x.ndim == 0:
+            raise ValueError("cannot accumulate on a scalar")
+        axis = axis % x.ndim
+        inner_op = _lib.GFB_ADD if op in (_lib.GFB_ADD, _lib.GFB_SUB) else _lib.GFB_MUL
+        if x.shape[axis] == 0:
+            return x.astype(dtype).view(cls)
+        if op in (_lib.GFB_ADD, _lib.GFB_MUL) or x.shape[axis] == 1:
+            return np.asarray(cls._fold(inner_op, x, axis, True, dtype)).view(cls)
+        # a0 - (a1 + ... + ak): running fold of the tail, then one element-wise pass against the broadcast head
+        tail = x[(slice(None),) * axis + (slice(1, None),)]
+        run = np.asarray(cls._fold(inner_op, tail, axis, True, dtype))
+        head = np.take(x, [0], axis=axis)
+        rest = np.asarray(cls._binary(op, np.broadcast_to(head, run.shape).view(cls), run.view(cls), dtype))
+        return np.concatenate([head.astype(dtype), rest], axis=axis).view(cls)
+
+    @classmethod
+    def _reduceat(cls, op, a, indices, axis, dtype):
+        """np.<ufunc>.reduceat (NumPy semantics: segment i is a[idx[i]:idx[i+1]], or the single element a[idx[i]] when
+        idx[i] >= idx[i+1]; the last segment runs to the end)."""
+        if cls._wide:
+            raise NotImplementedError(f"ufunc.reduceat is not implemented over {cls.name} (elements wider than 64 bits).")
+        x = np.asarray(a.view(np.ndarray))
+        idx = np.asarray(indices)
+        if idx.ndim != 1 or not np.issubdtype(idx.dtype, np.integer):
+            raise TypeError("Argument 'indices' of reduceat must be a 1-D integer array.")
+        axis = axis % x.ndim
+        n = x.shape[axis]
+        idx = idx.astype(np.int64)
+        if idx.size and (idx.min() < 0 or idx.max() >= n):
+            raise IndexError(f"index {int(idx.max() if idx.max() >= n else idx.min())} out-of-bounds in {('add', 'subtract', 'multiply', 'divide')[op]}.reduceat [0, {n})")
+        xm = np.ascontiguousarray(np.moveaxis(cls._prep(x, dtype), axis, -1))  # [lines][n]
+        lines = xm.size // n if n else 0
+        nseg = idx.size
+        end = np.concatenate([idx[1:], [n]]) if nseg else idx
+        end = np.where(end > idx, end, idx + 1)  # single-element segments
+        inner_op = _lib.GFB_ADD if op in (_lib.GFB_ADD, _lib.GFB_SUB) else _lib.GFB_MUL
+        out = _pinned.empty(xm.shape[:-1] + (nseg,), dtype)
+        if out.size:
+            offs = (np.arange(lines, dtype=np.int64) * n)[:, None]
+            lib = _lib.lib()
+            if op in (_lib.GFB_ADD, _lib.GFB_MUL):
+                start_all = np.ascontiguousarray((offs + idx[None, :]).reshape(-1))
+                end_all = np.ascontiguousarray((offs + end[None, :]).reshape(-1))
+                st = lib.gfb_fold_segments_host(cls._handle(), inner_op, cls._elem_bytes(dtype), xm.ctypes.data, xm.size,
+                                                start_all.ctypes.data, end_all.ctypes.data, out.ctypes.data, start_all.size)
+                _lib.check(st, "gfb_fold_segments_host")
+            else:
+                # left fold a[s] (op) (a[s+1] + ... ): fold the tails of the segments that have one, then one pass
+                flat = xm.reshape(lines, n)
+                heads = flat[:, idx]
+                res = heads.copy()
+                has_tail = end - idx > 1
+                if has_tail.any():
+                    ts = np.ascontiguousarray((offs + idx[None, has_tail] + 1).reshape(-1))
+                    te = np.ascontiguousarray((offs + end[None, has_tail]).reshape(-1))
+                    tails = np.empty(ts.size, dtype=dtype)
+                    st = lib.gfb_fold_segments_host(cls._handle(), inner_op, cls._elem_bytes(dtype), xm.ctypes.data, xm.size,
+                                                    ts.ctypes.data, te.ctypes.data, tails.ctypes.data, ts.size)
+                    _lib.check(st, "gfb_fold_segments_host")
+                    hh = np.ascontiguousarray(heads[:, has_tail]).reshape(-1)
+                    res[:, has_tail] = np.asarray(cls._binary(op, hh.view(cls), tails.view(cls), dtype)).reshape(lines, -1)
+                out[...] = res.reshape(out.shape)
+        return np.moveaxis(np.asarray(out), -1, axis).view(cls)
+
+    @classmethod
+    def _at(cls, kind, op, a, indices, b):
+        """np.<ufunc>.at(a, indices[, b]): unbuffered in-place a[indices] = op(a[indices], b).  An index that occurs k
+        times is updated k times, in order: the selected positions are processed in rounds (round r takes the r-th
+        occurrence of every index, so positions are unique inside a round) of gather -> element-wise kernel -> scatter."""
+        if not isinstance(a, cls):
+            raise TypeError(f"The first operand of ufunc.at must be a {cls.name} array, not {type(a)}.")
+        dtype = a.dtype
+        flat_index = np.arange(a.size, dtype=np.int64).reshape(a.shape)[indices]
+        pos = np.atleast_1d(np.asarray(flat_index)).reshape(-1)
+        if kind != "unary":
+            if b is None:
+                raise ValueError("second operand needed for ufunc")
+            if kind == "binary":
+                if isinstance(b, (int, np.integer)) and op == _lib.GFB_MUL:
+                    b = cls(int(b) % cls.characteristic, dtype=dtype)
+                elif not isinstance(b, cls):
+                    raise TypeError(f"Operation requires both operands to be instances of {cls.name}, not {type(b)}.")
+            elif isinstance(b, FieldArray):
+                raise TypeError(f"Operation 'power' requires the second operand to be an integer array, not {type(b)}.")
+            bb = np.broadcast_to(np.asarray(b.view(np.ndarray) if isinstance(b, np.ndarray) else b), np.shape(flat_index)).reshape(-1)
+        if pos.size == 0:
+            return None
+        order = np.argsort(pos, kind="stable")
+        sp = pos[order]
+        first = np.concatenate([[True], sp[1:] != sp[:-1]])
+        group_start = np.maximum.accumulate(np.where(first, np.arange(sp.size), 0))
+        rank = np.arange(sp.size) - group_start
+        target = a.view(np.ndarray)
+        if not target.flags.c_contiguous:
+            raise ValueError("ufunc.at on the CUDA backend needs a C-contiguous array.")
+        flat = target.reshape(-1)
+        for r in range(int(rank.max()) + 1):
+            sel = order[rank == r]
+            p = pos[sel]
+            vals = np.ascontiguousarray(flat[p]).view(cls)
+            if kind == "unary":
+                res = cls._unary(op, vals, dtype)
+            elif kind == "power":
+                res = cls._power([vals, np.ascontiguousarray(bb[sel])], [0, 1], dtype)
+            else:
+                res = cls._binary(op, vals, np.ascontiguousarray(bb[sel]).view(cls) if not cls._wide else bb[sel].view(cls), dtype)
+            flat[p] = np.asarray(res).reshape(-1)
+        return None
 
     # ------------------------------------------------------------------------------ array functions
     def __array_function__(self, func, types, args, kwargs):

@@ -49,6 +49,11 @@ SIGNATURES = {
     "gfb_unary_host": (_int, [_vp, _int, _int, _vp, _vp, _sz]),
     "gfb_power_host": (_int, [_vp, _int, _vp, _vp, _vp, _sz]),
     "gfb_power_scalar_host": (_int, [_vp, _int, _vp, _i64, _vp, _sz]),
+    "gfb_fold_workspace_bytes": (_sz, [_int, _sz, _sz, _sz]),
+    "gfb_fold": (_int, [_vp, _int, _int, _int, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "gfb_fold_host": (_int, [_vp, _int, _int, _int, _vp, _vp, _sz, _sz, _sz]),
+    "gfb_fold_segments": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gfb_fold_segments_host": (_int, [_vp, _int, _int, _vp, _sz, _vp, _vp, _vp, _sz]),
     "gfb_ntt_plan_create": (_int, [C.POINTER(_vp), _vp, _sz, _u64, _u64]),
     "gfb_ntt_plan_destroy": (None, [_vp]),
     "gfb_ntt_workspace_bytes": (_sz, [_vp, _int, _sz]),

@@ -36,6 +36,7 @@ void set_last_error(const char* what, cudaError_t err);
     } while (0)
 
 int sm_count();  // multiprocessors of the current device (cached)
+void conv_cache_drop(gfb_field* f);  // gfb_linalg.cu: transform plans cached for gfb_convolve over this field
 
 // ----------------------------------------------------------------------------------------
 // 128-bit element for GF(2^m), 64 < m <= 128
@@ -554,6 +555,8 @@ struct gfb_field {
     uint16_t* d_log;
     uint16_t* h_exp;
     uint16_t* h_log;
+    // 256 x 256 product + quotient tables of a byte-sized GF(2^m) (gfb_ewise_tab8.cu), built on first use
+    uint8_t* d_tab8;
     // sticky error flag in mapped pinned host memory
     int* h_err;
     int* d_err;

@@ -45,6 +45,8 @@ static gfb_status binary_dispatch(gfb_field* f, int op, int mode, int eb, const 
             return ewise_binary_barrett(f->prime_barrett(), op, mode, eb, a, b, s_lo, s_hi, out, n, f->d_err, st);
         case IMPL_BIN_LUT:
             if (mode != MODE_AA && s_lo >= f->order_lo) return GFB_ERR_BAD_ARG;
+            if (tab8_applies(f, op, eb, a, mode == MODE_AA ? b : a, out))
+                return ewise_binary_tab8(f, op, mode, a, b, s_lo, out, n, st);
             return ewise_binary_lut(f->bin_lut(), op, mode, eb, a, b, s_lo, s_hi, out, n, f->d_err, st);
         case IMPL_BIN_CALC:
             if (mode != MODE_AA && f->degree < 64 && s_lo >= f->order_lo) return GFB_ERR_BAD_ARG;

@@ -247,6 +247,8 @@ gfb_status gfb_field_create(gfb_field** out, int kind, uint64_t order_lo, int de
 
 void gfb_field_destroy(gfb_field* f) {
     if (!f) return;
+    gfb::conv_cache_drop(f);
+    if (f->d_tab8) cudaFree(f->d_tab8);
     if (f->d_exp) cudaFree(f->d_exp);
     if (f->d_log) cudaFree(f->d_log);
     if (f->h_err) cudaFreeHost(f->h_err);

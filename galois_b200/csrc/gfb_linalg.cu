@@ -9,6 +9,10 @@
 //
 // These are integer kernels; the GF(p) inner products accumulate unreduced 64-bit products in a
 // 128-bit accumulator and reduce once per output.  No tensor cores (exact integer work).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "gfb_common.cuh"
 #include "gfb_dot.cuh"
 
@@ -186,6 +190,135 @@ static gfb_status matmul_by_width(F f, int eb, const void* A, const void* B, voi
     return GFB_ERR_BAD_ARG;
 }
 
+// ----------------------------------------------------------------------------------------
+// NTT-based convolution over GF(p) when the padded length L = 2^k divides p - 1 (e.g. p = 998244353):
+//   c = INTT_L( NTT_L(a padded) .* NTT_L(b padded) ),  L >= na + nb - 1.
+// The field result is unique, so this is bit-identical to the reference's schoolbook / np.convolve paths
+// (_domains/_function.py:136-167) whichever primitive L-th root is used; it replaces O(na nb) work by three
+// transforms on the kernels of gfb_ntt.cu.
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_conv_pad(const T* __restrict__ a, size_t na, const T* __restrict__ b, size_t nb, uint32_t* __restrict__ AB,
+                           size_t L) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * L) return;
+    const size_t j = i < L ? i : i - L;
+    uint32_t v = 0;
+    if (i < L) {
+        if (j < na) v = (uint32_t)a[j];
+    } else if (j < nb) {
+        v = (uint32_t)b[j];
+    }
+    AB[i] = v;
+}
+
+template <typename T>
+__global__ void k_conv_unpad(const uint32_t* __restrict__ A, T* __restrict__ out, size_t nc) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nc) out[i] = (T)A[i];
+}
+
+struct ConvPlans {
+    gfb_ntt_plan* fwd;
+    gfb_ntt_plan* inv;
+};
+static std::mutex g_conv_mu;
+static std::map<std::pair<gfb_field*, size_t>, ConvPlans> g_conv_plans;
+
+static uint32_t host_pow_u32(uint32_t b, unsigned long long e, uint32_t p) {
+    unsigned long long r = 1 % p, x = b % p;
+    while (e) {
+        if (e & 1) r = r * x % p;
+        x = x * x % p;
+        e >>= 1;
+    }
+    return (uint32_t)r;
+}
+
+void conv_cache_drop(gfb_field* f) {
+    std::lock_guard<std::mutex> lk(g_conv_mu);
+    for (auto it = g_conv_plans.begin(); it != g_conv_plans.end();) {
+        if (it->first.first == f) {
+            gfb_ntt_plan_destroy(it->second.fwd);
+            gfb_ntt_plan_destroy(it->second.inv);
+            it = g_conv_plans.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+// padded transform length, or 0 when the NTT route does not apply
+static size_t conv_ntt_length(const gfb_field* f, size_t na, size_t nb) {
+    if (f->kind != GFB_PRIME || f->p < 3 || f->p >= (1u << 31)) return 0;
+    const size_t nc = na + nb - 1;
+    const size_t small = na < nb ? na : nb;
+    if (small < 32 || nc < 1024) return 0;  // the schoolbook kernel wins on short operands
+    size_t L = 1;
+    while (L < nc) L <<= 1;
+    if (L > ((size_t)1 << 24) || ((unsigned long long)f->p - 1ull) % L != 0) return 0;
+    return L;
+}
+
+template <typename T>
+static gfb_status convolve_ntt_t(gfb_field* f, const T* a, size_t na, const T* b, size_t nb, T* out, size_t L,
+                                 cudaStream_t st) {
+    ConvPlans plans;
+    {
+        std::lock_guard<std::mutex> lk(g_conv_mu);
+        auto key = std::make_pair(f, L);
+        auto it = g_conv_plans.find(key);
+        if (it == g_conv_plans.end()) {
+            const uint32_t p = f->p;
+            const uint32_t omega = host_pow_u32((uint32_t)f->primitive_element, ((unsigned long long)p - 1ull) / L, p);
+            const uint32_t omega_inv = host_pow_u32(omega, (unsigned long long)p - 2ull, p);
+            const uint32_t scale = host_pow_u32((uint32_t)(L % p), (unsigned long long)p - 2ull, p);
+            ConvPlans np{nullptr, nullptr};
+            gfb_status rc = gfb_ntt_plan_create(&np.fwd, f, L, omega, 1);
+            if (rc == GFB_OK) rc = gfb_ntt_plan_create(&np.inv, f, L, omega_inv, scale);
+            if (rc != GFB_OK) {
+                gfb_ntt_plan_destroy(np.fwd);
+                gfb_ntt_plan_destroy(np.inv);
+                return rc;
+            }
+            it = g_conv_plans.emplace(key, np).first;
+        }
+        plans = it->second;
+    }
+    const size_t nc = na + nb - 1;
+    size_t ws_bytes = gfb_ntt_workspace_bytes(plans.fwd, 4, 2);
+    const size_t ws_inv = gfb_ntt_workspace_bytes(plans.inv, 4, 1);
+    if (ws_inv > ws_bytes) ws_bytes = ws_inv;
+    char* mem = nullptr;
+    GFB_CUDA_TRY(cudaMallocAsync((void**)&mem, 2 * L * sizeof(uint32_t) + ws_bytes + 256, st));
+    uint32_t* AB = (uint32_t*)mem;
+    void* ws = ws_bytes ? (void*)(mem + ((2 * L * sizeof(uint32_t) + 255) & ~(size_t)255)) : nullptr;
+    gfb_status rc = GFB_OK;
+    k_conv_pad<T><<<(unsigned)((2 * L + 255) / 256), 256, 0, st>>>(a, na, b, nb, AB, L);
+    rc = gfb_ntt_exec(plans.fwd, 4, AB, AB, 2, ws, st);
+    if (rc == GFB_OK) rc = gfb_binary(f, GFB_MUL, 4, AB, AB + L, AB, L, st);
+    if (rc == GFB_OK) rc = gfb_ntt_exec(plans.inv, 4, AB, AB, 1, ws, st);
+    if (rc == GFB_OK) {
+        k_conv_unpad<T><<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(AB, out, nc);
+        if (cudaGetLastError() != cudaSuccess) rc = GFB_ERR_CUDA;
+    }
+    cudaFreeAsync(mem, st);
+    return rc;
+}
+
+static gfb_status convolve_ntt(gfb_field* f, int eb, const void* a, size_t na, const void* b, size_t nb, void* out,
+                               size_t L, cudaStream_t st) {
+    switch (eb) {
+        case 1: return convolve_ntt_t<uint8_t>(f, (const uint8_t*)a, na, (const uint8_t*)b, nb, (uint8_t*)out, L, st);
+        case 2: return convolve_ntt_t<uint16_t>(f, (const uint16_t*)a, na, (const uint16_t*)b, nb, (uint16_t*)out, L, st);
+        case 4: return convolve_ntt_t<uint32_t>(f, (const uint32_t*)a, na, (const uint32_t*)b, nb, (uint32_t*)out, L, st);
+        case 8:
+            return convolve_ntt_t<unsigned long long>(f, (const unsigned long long*)a, na, (const unsigned long long*)b, nb,
+                                                      (unsigned long long*)out, L, st);
+    }
+    return GFB_ERR_BAD_ARG;
+}
+
 static bool width_ok(const gfb_field* f, int eb) {
     if (f->impl == IMPL_BIN_128) return eb == 16;
     if (eb != 1 && eb != 2 && eb != 4 && eb != 8) return false;
@@ -204,6 +337,7 @@ gfb_status gfb_convolve(gfb_field* f, int eb, const void* a, size_t na, const vo
     if (!f || !a || !b || !out || na == 0 || nb == 0) return GFB_ERR_BAD_ARG;
     if (!width_ok(f, eb)) return GFB_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (const size_t L = conv_ntt_length(f, na, nb)) return convolve_ntt(f, eb, a, na, b, nb, out, L, st);
     switch (f->impl) {
         case IMPL_PRIME_M31: return conv_by_width(f->prime_m31(), eb, a, na, b, nb, out, st);
         case IMPL_PRIME_BARRETT: return conv_by_width(f->prime_barrett(), eb, a, na, b, nb, out, st);

@@ -130,6 +130,26 @@ gfb_status gfb_power_host(gfb_field* f, int elem_bytes, const void* a, const int
 gfb_status gfb_power_scalar_host(gfb_field* f, int elem_bytes, const void* a, int64_t e, void* out,
                                  size_t n);
 
+/* ------------------------------------------------------------ ufunc methods ---- */
+/* np.<ufunc>.reduce / np.<ufunc>.accumulate on a field array: the reference forwards ufunc methods to the compiled
+ * DUFunc (UFunc dispatchers, _domains/_ufunc.py:349,403; tests/fields/test_numpy_ufuncs.py) — a serial fold with the
+ * field's add / multiply.  `a` is viewed as [outer][len][inner] (C order: any axis of an N-D array); op is GFB_ADD or
+ * GFB_MUL (subtract / divide folds are a0 - (a1 + ... ) and a0 / (a1 * ...): the caller composes them).
+ *   scan = 0: out[outer][inner]      = a[o][0][i] (op) a[o][1][i] (op) ...      (reduce)
+ *   scan = 1: out[outer][len][inner] = running fold along len                   (accumulate)
+ * The device variant needs gfb_fold_workspace_bytes() of scratch (0 for most shapes).  64 < degree fields: UNSUPPORTED. */
+size_t gfb_fold_workspace_bytes(int elem_bytes, size_t outer, size_t len, size_t inner);
+gfb_status gfb_fold(gfb_field* f, int op, int scan, int elem_bytes, const void* a, void* out, size_t outer, size_t len,
+                    size_t inner, void* workspace, void* stream);
+gfb_status gfb_fold_host(gfb_field* f, int op, int scan, int elem_bytes, const void* a, void* out, size_t outer, size_t len,
+                         size_t inner);
+/* np.<ufunc>.reduceat: out[s] = fold of a[start[s] .. end[s]) for n_seg non-empty segments of the 1-D array a
+ * (start / end: int64, device memory for the device variant). */
+gfb_status gfb_fold_segments(gfb_field* f, int op, int elem_bytes, const void* a, const int64_t* start, const int64_t* end,
+                             void* out, size_t n_seg, void* stream);
+gfb_status gfb_fold_segments_host(gfb_field* f, int op, int elem_bytes, const void* a, size_t n, const int64_t* start,
+                                  const int64_t* end, void* out, size_t n_seg);
+
 /* ----------------------------------------------------------------- NTT / INTT */
 /* Replaces fft_jit / ifft_jit (_domains/_function.py:170-392) behind galois.ntt/intt
  * (_ntt.py:16-278) and np.fft.fft/ifft on field arrays, and ADDS the batch dimension

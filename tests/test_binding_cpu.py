@@ -57,6 +57,18 @@ def stubbed(monkeypatch):
     monkeypatch.setattr(FieldArray, "_unary", classmethod(_unary))
     monkeypatch.setattr(FieldArray, "_power", classmethod(_power))
 
+    def _fold(cls, inner_op, x, axis, scan, dtype):
+        x = np.moveaxis(np.asarray(x).astype(np.int64), axis, -1)
+        acc = x[..., 0].copy()
+        outs = [acc.copy()]
+        for j in range(1, x.shape[-1]):
+            acc = ofield(cls).binary_op(inner_op, acc.reshape(-1), x[..., j].reshape(-1)).reshape(acc.shape)
+            outs.append(acc.copy())
+        res = np.moveaxis(np.stack(outs, axis=-1), -1, axis) if scan else acc
+        return res.astype(dtype)
+
+    monkeypatch.setattr(FieldArray, "_fold", classmethod(_fold))
+
     def convolve(field, a, b, mode="full"):
         c = ofield(field).convolve(np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64))
         return c.astype(a.dtype).view(field)
@@ -125,7 +137,10 @@ def test_dispatch_plumbing(stubbed, order):
     both(GF, lambda: x + 1)
     both(GF, lambda: x ** GF(2))
     both(GF, lambda: np.negative.reduce(x))
-    both(GF, lambda: np.multiply.accumulate(y[:20]))  # delegated to the reference DUFunc until the scan kernel lands
+    both(GF, lambda: np.multiply.accumulate(y[:20]))
+    both(GF, lambda: np.add.reduce(x))
+    both(GF, lambda: np.subtract.accumulate(x[:9]))
+    both(GF, lambda: np.add.reduce(x.reshape(10, 20), axis=1))
 
     def with_out():
         o = GF.Zeros(200, dtype=wide)

@@ -372,3 +372,26 @@ def test_row_reduce_slab_in_global_memory():
     B = G8.Random((6300, 40), seed=79)  # one-byte elements: 6300 rows exceed the slab as well
     F8 = oracle.Field.binary(8, 0x11D, alpha=2)
     assert eq(B.row_reduce(), F8.row_reduce(np.asarray(B))[0])
+
+
+@pytest.mark.parametrize("p,na,nb", [(998244353, 4096, 4096), (998244353, 1000, 33), (998244353, 5000, 7), (998244353, 30000, 20000),
+                                     (65537, 30000, 30000), (65537, 35000, 31000), (2**31 - 1, 3000, 2000), (7681, 300, 200),
+                                     (3329, 2000, 1500)])
+def test_convolve_ntt_route_matches_the_oracle(p, na, nb):
+    """np.convolve over GF(p): the NTT route (padded length 2^k | p - 1) and the schoolbook kernel give the reference's
+    field result (convolve_jit, _domains/_function.py:111-167), every storage width."""
+    import oracle
+
+    GF = gb.GF(p)
+    F = oracle.Field.prime(p)
+    rng = np.random.default_rng(na + nb)
+    a = rng.integers(0, p, na)
+    b = rng.integers(0, p, nb)
+    a[:3] = [p - 1, 0, 1]
+    want = F.convolve(a, b)
+    for dtype in GF.dtypes[:1] + GF.dtypes[-1:]:
+        got = np.convolve(GF(a, dtype=dtype), GF(b, dtype=dtype))
+        assert type(got) is GF and got.dtype == dtype
+        assert np.array_equal(np.asarray(got).astype(np.int64), want), (p, na, nb, dtype)
+    got = np.convolve(GF(b), GF(a))
+    assert np.array_equal(np.asarray(got).astype(np.int64), want)

@@ -591,3 +591,75 @@ def test_rs_low_rate_codes_vs_oracle(n, k):
         odec, onerr = ors.decode(R, E if n_era else None, threads=8)
         assert np.array_equal(nerr, onerr), (n, k, n_err, n_era)
         assert np.array_equal(np.asarray(dec), odec), (n, k, n_err, n_era)
+
+
+@pytest.mark.parametrize("name", ["GF(2^8)", "GF(31)", "GF(2147483647)", "GF(2^32)", "GF(3191)"])
+def test_ufunc_methods_reduce_accumulate_reduceat_at(name):
+    """np.<ufunc>.reduce / accumulate / reduceat / at (the reference forwards them to its DUFunc, _ufunc.py:349,403;
+    tests/fields/test_numpy_ufuncs.py): serial folds with the oracle's field operations as the expected values."""
+    GF = make_gf(name)
+    F = oracle_field(name)
+    rng = np.random.default_rng(5)
+    order = GF.order
+    ops = {np.add: F.add, np.subtract: F.sub, np.multiply: F.mul, np.true_divide: F.div}
+
+    def serial(fn, rows):  # running left fold along the last axis
+        rows = np.asarray(rows, dtype=np.int64)
+        acc = rows[..., 0].copy()
+        out = [acc.copy()]
+        for j in range(1, rows.shape[-1]):
+            acc = np.asarray(fn(acc.reshape(-1), rows[..., j].reshape(-1))).reshape(acc.shape)
+            out.append(acc.copy())
+        return np.stack(out, axis=-1)
+
+    for shape in [(7,), (1,), (3, 41), (5, 4, 6), (70000,), (2, 40000)]:
+        x = rng.integers(1, order, shape)
+        gx = GF(x)
+        for ufunc, fn in ops.items():
+            for axis in range(len(shape)):
+                want = np.moveaxis(serial(fn, np.moveaxis(x, axis, -1)), -1, axis)
+                got = ufunc.accumulate(gx, axis=axis)
+                assert type(got) is GF and got.dtype == gx.dtype
+                assert eq(got, want), (name, ufunc.__name__, shape, axis, "accumulate")
+                red = ufunc.reduce(gx, axis=axis)
+                assert eq(red, np.take(want, -1, axis=axis)), (name, ufunc.__name__, shape, axis, "reduce")
+    x = rng.integers(1, order, 50)
+    gx = GF(x)
+    idx = np.array([0, 7, 7, 3, 20, 49, 10])
+    for ufunc, fn in ops.items():
+        want = []
+        for i, s in enumerate(idx):
+            e = idx[i + 1] if i + 1 < len(idx) else len(x)
+            seg = x[s:e] if e > s else x[s:s + 1]
+            want.append(serial(fn, seg[None, :])[0, -1])
+        got = ufunc.reduceat(gx, idx)
+        assert type(got) is GF and eq(got, np.array(want)), (name, ufunc.__name__, "reduceat")
+    X2 = rng.integers(1, order, (4, 30))
+    got = np.add.reduceat(GF(X2), [0, 5, 5, 29], axis=1)
+    want = np.stack([serial(F.add, X2[:, 0:5])[:, -1], X2[:, 5], serial(F.add, X2[:, 5:29])[:, -1], X2[:, 29]], axis=1)
+    assert eq(got, want)
+    # at: repeated indices are applied once per occurrence, in order
+    for ufunc, fn in ops.items():
+        a = x.copy()
+        ga = GF(x)
+        ii = np.array([3, 3, 0, 49, 3, 7])
+        b = rng.integers(1, order, ii.size)
+        assert ufunc.at(ga, ii, GF(b)) is None
+        for k, i in enumerate(ii):
+            a[i] = fn(np.array([a[i]]), np.array([b[k]]))[0]
+        assert eq(ga, a), (name, ufunc.__name__, "at")
+    ga = GF(x)
+    np.negative.at(ga, [1, 1, 2])
+    want = x.copy()
+    want[2] = F.neg(np.array([x[2]]))[0]
+    assert eq(ga, want)
+    ga = GF(x)
+    np.power.at(ga, [0, 0, 5], np.array([3, 2, -1]))
+    want = x.copy()
+    want[0] = F.power(np.array([x[0]]), np.array([6]))[0]
+    want[5] = F.inv(np.array([x[5]]))[0]
+    assert eq(ga, want)
+    with pytest.raises(ValueError):
+        np.negative.reduce(gx)
+    with pytest.raises(ValueError):
+        np.power.accumulate(gx)
