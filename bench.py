@@ -433,6 +433,23 @@ class RsDecode:
     def gather_tensor(self):
         return self.dec.tensor.view(self.N, 255)
 
+    def secondary_roofline(self, units_per_sec):
+        """the decoder is bound by shared-memory table lookups, not HBM.  Field multiply-adds per codeword
+        (one product-table lookup each) against the SM's shared-memory rate of one 32-lane wavefront per clock."""
+        n, d1, v, u = 255, 32, self.n_err, self.n_era
+        ops = d1 * n + (d1 - u) * 2 * (v + 1) + n * (u + v + 1) + (v + u) * (d1 + u + v) + d1 * (v + 1) + d1 * (u + 1) * (u > 0)
+        sm_mhz = 1965.0
+        try:
+            sm_mhz = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["sm_max_mhz"])
+        except Exception:
+            pass
+        n_sm = self.torch.cuda.get_device_properties(0).multi_processor_count
+        peak = n_sm * sm_mhz * 1e6 * 32
+        ach = units_per_sec * ops
+        return {"bound": "smem", "achieved": ach, "peak": peak, "unit": "GF multiply-add/s", "frac": ach / peak,
+                "ops_per_unit": ops,
+                "note": "syndromes d1*n + Berlekamp-Massey + Chien n*(u+v+1) + Forney + the Omega / Gamma products; peak = SMs x 32 lanes x SM clock (one conflict-free shared-memory wavefront per clock)"}
+
     def check(self):
         assert bool((self.nerr == self.n_err).all()), "not every codeword reported the injected number of errors"
         assert bool((self.dec.tensor.view(self.N, 255) == self.C).all()), "decoded codewords differ from the originals"
@@ -1445,6 +1462,8 @@ def main():
     # dominant kernel: algorithmic bytes of one step on this rank / mean device time of one step
     achieved = work.units_per_step * cls.bytes_per_unit / (ms / 1e3 / args.steps) / 1e9
 
+    sec_roofline = work.secondary_roofline(work.units_per_step * args.steps / (ms / 1e3)) if hasattr(work, "secondary_roofline") else None
+
     # ---- end to end through the reference-facing API with HOST buffers (same metric): the reference's own classes
     #      with galois_b200.enable() when baseline/_ref is importable, else the mirror classes
     galois = load_reference() if not args.no_ref_e2e else None
@@ -1498,6 +1517,8 @@ def main():
                                "units_per_gpu_per_step": w.units_per_step,
                                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                             "kernel": ecls.kernel, "algorithmic_bytes_per_unit": ecls.bytes_per_unit}}
+                if hasattr(w, "secondary_roofline"):
+                    extras[key]["roofline_secondary"] = w.secondary_roofline(w.units_per_step * esteps / (ems / 1e3))
                 if world > 1 and ecls.scaling == "strong":
                     extras[key]["final_gather_ms"] = time_gather(w, world)
                 del w
@@ -1544,6 +1565,8 @@ def main():
                      "algorithmic_bytes_per_step": cls.bytes_per_unit * per_gpu_units},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    if sec_roofline is not None:
+        line["roofline_secondary"] = sec_roofline
     if port is not None and port is not cpu:
         line["cpu_port"] = port
     if med is not None:

@@ -35,6 +35,7 @@ GFB_EWISE_DECLARE(calc, BinaryCalc)
 GFB_EWISE_DECLARE(b128, Binary128)
 
 // byte-sized GF(2^m) multiply / divide through the 64 KiB product table (gfb_ewise_tab8.cu)
+gfb_status ensure_tab8(gfb_field* f, cudaStream_t st);  // builds f->d_tab8 (products, then quotients) on first use
 bool tab8_applies(const gfb_field* f, int op, int eb, const void* a, const void* b, const void* out);
 gfb_status ewise_binary_tab8(gfb_field* f, int op, int mode, const void* a, const void* b, uint64_t s, void* out, size_t n,
                              cudaStream_t st);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kTabThreads)
 }
 
 // build (once per field, on `st`) and return the device table
-static gfb_status ensure_tab8(gfb_field* f, cudaStream_t st) {
+gfb_status ensure_tab8(gfb_field* f, cudaStream_t st) {
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (f->d_tab8) return GFB_OK;

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "gfb_common.cuh"
+#include "gfb_ewise_api.cuh"
 #include "gfb_host.cuh"
 
 struct gfb_rs_code {
@@ -439,6 +440,8 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
     }
 }
 
+#include "gfb_rs_fast.cuh"
+
 static RsDev make_dev(const gfb_rs_code* rs) {
     RsDev d;
     d.n = rs->n;
@@ -608,6 +611,24 @@ gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t
     if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
     if (N == 0) return GFB_OK;
     RsDev d = make_dev(rs);
+    static const bool fast_on = [] {
+        const char* e = getenv("GFB_RS_FAST");
+        return !(e && e[0] == '0');
+    }();
+    if (fast_on && rs->d - 1 <= 32 && rs->d >= 2) {
+        // at most 32 parity symbols: the register-resident decoder on the field's product table (gfb_rs_fast.cuh)
+        gfb_status rc = ensure_tab8(rs->field, (cudaStream_t)stream);
+        if (rc != GFB_OK) return rc;
+        GFB_CUDA_TRY(cudaFuncSetAttribute(fastrs::k_rs_decode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fastrs::kSmemBytes));
+        size_t grid = (N + fastrs::kWarps - 1) / fastrs::kWarps;
+        const size_t cap = (size_t)sm_count() * 2;  // two 512-thread CTAs (64 KiB table each) per SM
+        if (grid > cap) grid = cap;
+        fastrs::k_rs_decode_fast<<<(unsigned)grid, fastrs::kThreadsPerCta, fastrs::kSmemBytes, (cudaStream_t)stream>>>(
+            d, rs->field->d_tab8, received, erasures, ns, decoded, (long long*)n_errors, N);
+        GFB_CUDA_TRY(cudaGetLastError());
+        return GFB_OK;
+    }
     const size_t smem = kExpSize + 256 * sizeof(uint16_t) + (size_t)kRsWarps * kScratchArrays * kMaxN;
     GFB_CUDA_TRY(cudaFuncSetAttribute(k_rs_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_rs_decode<<<rs_grid(N), kRsThreads, smem, (cudaStream_t)stream>>>(d, received, erasures, ns, decoded,
