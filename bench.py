@@ -1245,7 +1245,78 @@ class MatmulRs:
     cpu_sample = "2000 rows per thread (matmul_jit's triple loop with EXP/LOG lookups), rows over OpenMP threads"
 
 
-WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMixed, "convolve": Convolve,
+class NttSharded:
+    """SURVEY.md §8f rank 3 (second half): ONE 2^26-point NTT over GF(998244353) spread over the ranks — local column pass,
+    NCCL all-to-all, local row pass (galois_b200._dist.ShardedNtt).  The only workload whose curve a collective can limit;
+    `phases_ms` names the all-to-all's share."""
+
+    metric, unit, dtype, scaling = "ntt_2p26_sharded_per_sec", "NTT/s", "uint32", "strong"
+    kernel = "k_ntt_* (column pass) -> all_to_all_single (NCCL) -> k_ntt_* (row pass)"
+    LOG_N = 26
+    bytes_per_unit = 2 * 4 * 2**26
+
+    def __init__(self, rank, world, batch=None):
+        import torch
+
+        import galois_b200 as gb
+        from galois_b200._dist import ShardedNtt
+
+        self.gb, self.torch = gb, torch
+        self.GF = gb.GF(P_NTT)
+        self.N = 1 << self.LOG_N
+        self.sh = ShardedNtt(self.GF, self.N)
+        self.name = f"one 2^{self.LOG_N}-point NTT over GF(998244353) sharded over {world} GPU(s) (column slabs in, row slabs out)"
+        # two impulses: X[k] = w^(j0 k) + 5 w^(j1 k) checks every index map and twiddle at full size
+        self.j0, self.j1 = 12345677 % self.N, (3 * self.N // 7) | 1
+        g = torch.Generator(device="cuda").manual_seed(17)
+        slab = torch.randint(0, P_NTT, (self.sh.n1, self.sh.cols), dtype=torch.int32, device="cuda", generator=g)
+        self.x = gb.DeviceArray(self.GF, slab.view(torch.uint8).reshape(-1), (self.sh.n1, self.sh.cols), np.uint32)
+        self.units_per_step = 1 if rank == 0 else 0  # one transform for the whole job
+        type(self).bytes_per_unit = 2 * 4 * self.N // world  # per-GPU share of the compulsory traffic (roofline is per GPU)
+        self.launches_per_step = 8
+        self.h2d = self.d2h = 0
+        self.phases = []
+
+    def step(self):
+        self.out = self.sh(self.x)
+        self.phases.append(dict(self.sh.timings))
+
+    def check(self):
+        torch, sh, p = self.torch, self.sh, P_NTT
+        imp = torch.zeros((sh.n1, sh.n2), dtype=torch.int32, device="cuda")
+        imp.view(-1)[self.j0] = 1
+        imp.view(-1)[self.j1] = 5
+        slab = imp[:, sh.rank * sh.cols:(sh.rank + 1) * sh.cols].contiguous()
+        X = sh(self.gb.DeviceArray(self.GF, slab.view(torch.uint8).reshape(-1), (sh.n1, sh.cols), np.uint32))
+        got = X.tensor.view(torch.int32).view(sh.rows, sh.n2)
+        idx = sh.output_indices()
+        sel = torch.randint(0, idx.numel(), (4096,), device="cuda")
+        ks = idx.reshape(-1)[sel].cpu().numpy().astype(object)
+        w = sh.omega
+        want = [(pow(w, int(self.j0 * k % self.N), p) + 5 * pow(w, int(self.j1 * k % self.N), p)) % p for k in ks]
+        assert got.reshape(-1)[sel].cpu().numpy().astype(np.int64).tolist() == want, "sharded NTT differs from w^(jk)"
+
+    def e2e_setup(self, galois=None):
+        self.e2e_units = None
+
+    ref_setup = None
+
+    def cpu_step(self, threads):
+        import oracle
+
+        F = oracle.Field.prime(P_NTT)
+        if not hasattr(self, "cx"):
+            self.cN = 1 << 22
+            self.cx = np.random.default_rng(3).integers(0, P_NTT, self.cN, dtype=np.int64)
+            self.comega = int(self.GF.primitive_root_of_unity(self.cN))
+        F.fft(self.cx, self.comega)
+        return self.cN / self.N  # fraction of a 2^26-point transform by element count (log factor ignored: 22 vs 26 stages)
+
+    cpu_sample = "one 2^22-point transform (1/16 of the elements), one thread, counted as 1/16 transform"
+    cpu_cores = 1
+
+
+WORKLOADS.update({"matinv": MatInv, "poly_roots": PolyRoots, "fft_mixed": FftMixed, "convolve": Convolve, "ntt_sharded": NttSharded,
                   "convolve_gf256": ConvolveGf256, "matmul_rs": MatmulRs})
 
 
@@ -1571,6 +1642,9 @@ def main():
         line["cpu_port"] = port
     if med is not None:
         line["value_at_median"] = units_all / (med / 1e3)
+    if getattr(work, "phases", None):
+        ph = work.phases[-args.steps:]
+        line["phases_ms"] = {k: statistics.median(d[k] for d in ph) for k in ph[0]}
     if gather_ms is not None:
         line["final_gather_ms"] = gather_ms
     if extras:

@@ -9,6 +9,7 @@
 //   array (op) array : the 64 KiB table;  array (op) scalar / scalar (op) array : its 256-entry row or column.
 // Algorithmic bytes per element: 3.  Division flags a zero divisor with the has-zero-byte test
 // on the packed operand words.
+#include <atomic>
 #include <mutex>
 
 #include "gfb_common.cuh"
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kTabThreads)
 
 // build (once per field, on `st`) and return the device table
 gfb_status ensure_tab8(gfb_field* f, cudaStream_t st) {
+    if (f->d_tab8) return GFB_OK;
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (f->d_tab8) return GFB_OK;
@@ -214,13 +216,19 @@ gfb_status ewise_binary_tab8(gfb_field* f, int op, int mode, const void* a, cons
     if (mode == MODE_AA) {
         const size_t cap = (size_t)sm_count() * 3;  // three 64 KiB tables fit one SM
         if (blocks > cap) blocks = cap;
-        if (op == GFB_MUL) {
+        // the 64 KiB opt-in is a per-device function attribute: set it once per device (the call costs microseconds of host
+        // time, which is what a 1e6-element launch is made of)
+        static std::atomic<unsigned long long> attr_done{0};
+        const unsigned long long bit = 1ull << (f->device & 63);
+        if (!(attr_done.load(std::memory_order_acquire) & bit)) {
             GFB_CUDA_TRY(cudaFuncSetAttribute(k_tab8_aa<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabBytes));
-            k_tab8_aa<false><<<(unsigned)blocks, kTabThreads, kTabBytes, st>>>(f->d_tab8, A, (const uint8_t*)b, O, n, f->d_err);
-        } else {
             GFB_CUDA_TRY(cudaFuncSetAttribute(k_tab8_aa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabBytes));
-            k_tab8_aa<true><<<(unsigned)blocks, kTabThreads, kTabBytes, st>>>(f->d_tab8, A, (const uint8_t*)b, O, n, f->d_err);
+            attr_done.fetch_or(bit, std::memory_order_release);
         }
+        if (op == GFB_MUL)
+            k_tab8_aa<false><<<(unsigned)blocks, kTabThreads, kTabBytes, st>>>(f->d_tab8, A, (const uint8_t*)b, O, n, f->d_err);
+        else
+            k_tab8_aa<true><<<(unsigned)blocks, kTabThreads, kTabBytes, st>>>(f->d_tab8, A, (const uint8_t*)b, O, n, f->d_err);
     } else {
         const size_t cap = (size_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;

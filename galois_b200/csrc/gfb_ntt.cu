@@ -732,25 +732,50 @@ static bool fused_enabled() {
     return on;
 }
 
-template <bool LAZY>
-static gfb_status run_fused(gfb_ntt_plan* pl, const uint32_t* x, uint32_t* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+template <bool LAZY, int W>
+static gfb_status run_fused_w(gfb_ntt_plan* pl, const uint32_t* x, uint32_t* y, size_t batch, uint32_t* ws, cudaStream_t st) {
     using namespace fused;
+    using C = Cfg<W>;
     Mod<LAZY> md{pl->p, pl->p * 2u};
     const Radix32Roots rt = roots_of(pl);
-    const size_t kMaxBatch = (size_t)1 << 24;  // tickets are 32-bit: 128 per transform
+    const size_t kMaxBatch = (size_t)1 << 23;  // tickets are 32-bit: 2 * 1024 / W per transform
+    static const unsigned lag_cfg = [] {
+        const char* e = getenv("GFB_NTT_LAG");
+        const int v = e ? atoi(e) : 0;
+        return (unsigned)(v >= 1 && v < (int)kRingMax ? v : (int)kLagDefault);
+    }();
+    static const unsigned ring_cfg = [] {
+        const char* e = getenv("GFB_NTT_RING");
+        const int v = e ? atoi(e) : 0;
+        return (unsigned)(v >= 2 && v <= (int)kRingMax ? v : (int)kRingDefault);
+    }();
+    const unsigned ring_want = ring_cfg > lag_cfg ? ring_cfg : lag_cfg + 1;  // a slot is recycled only after its pass 2
     for (size_t off = 0; off < batch; off += kMaxBatch) {
         const size_t cnt = batch - off < kMaxBatch ? batch - off : kMaxBatch;
-        const unsigned ring = (unsigned)(cnt < kRing ? cnt : kRing);
+        const unsigned ring = (unsigned)(cnt < ring_want ? cnt : ring_want);
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + ((size_t)ring << 20));
         GFB_CUDA_TRY(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl) + 2 * cnt * sizeof(unsigned int), st));
-        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_fused<LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        size_t grid = (size_t)sm_count();
-        if (grid > cnt * 2 * kTilesPerPass) grid = cnt * 2 * kTilesPerPass;
-        k_ntt_fused<LAZY><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(md, rt, pl->d_zt, pl->d_tw4, x + (off << 20),
-                                                                          y + (off << 20), ws, ctrl, (unsigned)cnt, ring);
+        GFB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_fused<LAZY, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)C::kSmemBytes));
+        size_t grid = (size_t)sm_count() * (W == 16 ? 1 : 2);
+        if (grid > cnt * 2 * C::kTilesPerPass) grid = cnt * 2 * C::kTilesPerPass;
+        k_ntt_fused<LAZY, W><<<(unsigned)grid, C::kThreads, C::kSmemBytes, st>>>(
+            md, rt, pl->d_zt, pl->d_tw4, x + (off << 20), y + (off << 20), ws, ctrl, (unsigned)cnt, ring, lag_cfg);
         GFB_CUDA_TRY(cudaGetLastError());
     }
     return GFB_OK;
+}
+
+// tile width: 16 transforms per tile and one CTA per SM, or 8 and two (GFB_NTT_TILE)
+template <bool LAZY>
+static gfb_status run_fused(gfb_ntt_plan* pl, const uint32_t* x, uint32_t* y, size_t batch, uint32_t* ws, cudaStream_t st) {
+    static const int tile_w = [] {
+        const char* e = getenv("GFB_NTT_TILE");
+        const int v = e ? atoi(e) : 0;
+        return v == 8 || v == 16 ? v : 16;
+    }();
+    if (tile_w == 8) return run_fused_w<LAZY, 8>(pl, x, y, batch, ws, st);
+    return run_fused_w<LAZY, 16>(pl, x, y, batch, ws, st);
 }
 
 template <typename T, bool LAZY>

@@ -32,35 +32,18 @@
 
 namespace fused {  // (inside namespace gfb)
 
-constexpr int kComputeThreads = 512;
-constexpr int kThreads = kComputeThreads + 64;  // + load warp + store warp
+// W = transforms per tile (tile = W x 1024 words): 16 -> one 576-thread CTA per SM (3 x 64 KB tiles), 8 -> two 320-thread
+// CTAs per SM (3 x 32 KB tiles each) whose phases drift apart, which mixes the ALU / FMA / LSU demand of an SM.
 constexpr int kStages = 3;
-constexpr int kTileWords = 16 * 1024;  // 64 KB
-constexpr unsigned kLag = 3;           // pass 2 of transform T is queued kLag transforms behind its pass 1
-constexpr unsigned kRing = 8;          // intermediate ring (transforms); must exceed kLag
-constexpr unsigned kTilesPerPass = 64;
-constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s at 1.9 GHz
-
-enum : int { TASK_P1 = 0, TASK_P2 = 1, TASK_DONE = 2 };
-
-struct Ctrl {  // device memory, zeroed before every launch; followed by cnt1[batch], cnt2[batch]
-    unsigned int ticket;
-    unsigned int error;
-    unsigned int pad[2];
-};
-
-struct Desc {
-    int type;
-    int tile;
-    unsigned transform;
-    unsigned slot;
-};
-
-constexpr size_t kSmemTiles = (size_t)kStages * kTileWords * sizeof(uint32_t);  // 196608
-constexpr size_t kSmemZt = 1024 * sizeof(uint2);                                 // 8192
-constexpr size_t kSmemBytes = kSmemTiles + kSmemZt + 256;
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+template <int W>
+struct Cfg {
+    static constexpr int kComputeThreads = W * 32;
+    static constexpr int kThreads = kComputeThreads + 64;  // + load warp + store warp
+    static constexpr int kTileWords = W * 1024;
+    static constexpr unsigned kTilesPerPass = 1024 / W;
+    static constexpr int kTPerWarp = 32 / W;                // sub-transform indices t that share a warp
+    static constexpr int kSigmaMask = kTPerWarp - 1;        // exchange swizzle: row (t ^ (k1 & mask))
+    static // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -115,7 +98,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void compute_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -132,8 +118,8 @@ __device__ __forceinline__ void wait_counter(const unsigned int* cnt, unsigned i
 }
 
 // block number -> (pass, transform): P1(0..L-1), then P1(L) P2(0) P1(L+1) P2(1) ..., then the last L pass-2 blocks
-__device__ __forceinline__ void decode_block(unsigned n, unsigned batch, int& type, unsigned& transform) {
-    const unsigned L = kLag < batch ? kLag : batch;
+__device__ __forceinline__ void decode_block(unsigned n, unsigned batch, unsigned lag, int& type, unsigned& transform) {  // n = ticket / tiles-per-pass
+    const unsigned L = lag < batch ? lag : batch;
     if (n < L) {
         type = TASK_P1;
         transform = n;
@@ -151,76 +137,81 @@ __device__ __forceinline__ void decode_block(unsigned n, unsigned batch, int& ty
 }
 
 // ---- the compute rounds ------------------------------------------------------------------------------------------------
-// tile[j*16 + col]: j = index along the 1024-point transform, col = which of the tile's 16 transforms.
+// tile[j*W + col]: j = index along the 1024-point transform, col = which of the tile's W transforms.
 // Round A: thread (w, t) transforms x[32 a + t], a < 32, multiplies Y[k1] by zeta^(t k1) and parks it at
-// row 32 k1 + (t ^ (k1 & 1)) (the XOR keeps round B's column walk on distinct banks).  `col_read` is the column the
-// inputs sit in (pass 2 tiles arrive with the columns XOR-permuted by the row index), `w` the column the outputs use.
-template <bool LAZY>
+// row 32 k1 + (t ^ sigma(k1)), sigma(k1) = k1 & (32/W - 1) (the XOR keeps round B's column walk on distinct banks and
+// only permutes rows among the t's of one warp).  `col_read` is the column the inputs sit in (pass 2 tiles arrive with
+// the columns XOR-permuted by the row index), `w` the column the outputs use.
+template <bool LAZY, int W>
 __device__ __forceinline__ void round_a(uint32_t* __restrict__ tile, int t, int col_read, int w, const Mod<LAZY>& md,
                                         const Radix32Roots& rt, const uint2* __restrict__ zt_s) {
+    constexpr int M = Cfg<W>::kSigmaMask;
     uint32_t v[32];
-    const uint32_t* in = tile + t * 16 + col_read;
+    const uint32_t* in = tile + t * W + col_read;
 #pragma unroll
-    for (int a = 0; a < 32; ++a) v[brev5(a)] = in[a * 512];
+    for (int a = 0; a < 32; ++a) v[brev5(a)] = in[a * 32 * W];
     radixR<LAZY, 5, true>(v, md, rt);
-    __syncwarp();  // the partner lanes (t ^ 1, any column) have consumed the rows this thread is about to overwrite
-    uint32_t* out_even = tile + t * 16 + w;
-    uint32_t* out_odd = tile + (t ^ 1) * 16 + w;
-    out_even[0] = LAZY ? Mod<LAZY>::csub(v[0], md.p2) : v[0];
+    __syncwarp();  // the partner lanes (t ^ sigma, any column) have consumed the rows this thread is about to overwrite
+    uint32_t* out[M + 1];
+#pragma unroll
+    for (int sg = 0; sg <= M; ++sg) out[sg] = tile + (t ^ sg) * W + w;
+    out[0][0] = LAZY ? Mod<LAZY>::csub(v[0], md.p2) : v[0];
     const uint2* z = zt_s + t;
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
         const uint2 zz = z[k1 * 32];
-        const uint32_t val = md.mul(v[k1], zz.x, zz.y);
-        if (k1 & 1)
-            out_odd[k1 * 512] = val;
-        else
-            out_even[k1 * 512] = val;
+        out[k1 & M][k1 * 32 * W] = md.mul(v[k1], zz.x, zz.y);
     }
 }
 
 // Round B loads: thread (w, k1) gathers Y[b], b < 32, of its inner transform k1 (bit-reversed into v)
+template <int W>
 __device__ __forceinline__ void round_b_load(const uint32_t* __restrict__ tile, int k1, int w, uint32_t (&v)[32]) {
-    const int odd = k1 & 1;
-    const uint32_t* base = tile + k1 * 512 + w;
-    const uint32_t* pe = base + odd * 16;  // even b sits at row b ^ odd = b + odd
-    const uint32_t* po = base - odd * 16;  // odd b sits at row b - odd
+    constexpr int M = Cfg<W>::kSigmaMask;
+    const int sg = k1 & M;
+    const uint32_t* base = tile + k1 * 32 * W + w;
+    const uint32_t* p[M + 1];  // p[r] addresses row (r ^ sigma) of the group of M + 1 rows
 #pragma unroll
-    for (int b = 0; b < 32; ++b) v[brev5(b)] = (b & 1) ? po[b * 16] : pe[b * 16];
+    for (int r = 0; r <= M; ++r) p[r] = base + (r ^ sg) * W;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) v[brev5(b)] = p[b & M][(b & ~M) * W];
 }
 
-template <bool LAZY>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool LAZY, int W>
+__global__ void __launch_bounds__(Cfg<W>::kThreads, W == 16 ? 1 : 2)
     k_ntt_fused(Mod<LAZY> md, Radix32Roots rt, const uint2* __restrict__ zt, const uint2* __restrict__ tw4,
                 const uint32_t* __restrict__ x, uint32_t* __restrict__ y, uint32_t* __restrict__ ws, Ctrl* ctrl,
-                unsigned batch, unsigned ring) {
+                unsigned batch, unsigned ring, unsigned lag) {
+    using C = Cfg<W>;
+    constexpr int kTileWords = C::kTileWords;
+    constexpr unsigned TP = C::kTilesPerPass;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* bufs = reinterpret_cast<uint32_t*>(smem_raw);
-    uint2* zt_s = reinterpret_cast<uint2*>(smem_raw + kSmemTiles);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kSmemTiles + kSmemZt);
+    uint2* zt_s = reinterpret_cast<uint2*>(smem_raw + C::kSmemTiles);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::kSmemTiles + 1024 * sizeof(uint2));
     uint64_t* full = bars;         // [kStages] tile landed (32 arrivals of the load warp + tx bytes)
-    uint64_t* staged = bars + 3;   // [kStages] compute finished with the tile (512 arrivals)
+    uint64_t* staged = bars + 3;   // [kStages] compute finished with the tile (W*32 arrivals)
     uint64_t* empty = bars + 6;    // [kStages] tile buffer recycled (1 arrival of the store warp)
     Desc* desc = reinterpret_cast<Desc*>(bars + 12);
     unsigned int* cnt1 = reinterpret_cast<unsigned int*>(ctrl + 1);
     unsigned int* cnt2 = cnt1 + batch;
     unsigned int* err = &ctrl->error;
     const int tid = threadIdx.x;
-    const unsigned total = batch * 2u * kTilesPerPass;
+    const unsigned total = batch * 2u * TP;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 32);
-            mbar_init(&staged[s], kComputeThreads);
+            mbar_init(&staged[s], C::kComputeThreads);
             mbar_init(&empty[s], 1);
         }
         fence_mbar_init();
         fence_proxy_async();
     }
-    for (int i = tid; i < 1024; i += kThreads) zt_s[i] = __ldg(zt + i);
+    for (int i = tid; i < 1024; i += C::kThreads) zt_s[i] = __ldg(zt + i);
     __syncthreads();
 
-    if (tid >= kComputeThreads + 32) {
+    if (tid >= C::kComputeThreads + 32) {
         // ================================================================== store warp
         const int lane = tid & 31;
         for (unsigned it = 0;; ++it) {
@@ -231,12 +222,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (d.type == TASK_DONE) break;
             mbar_wait(&staged[b], ph, err, 0x20u + b);
             if (d.type == TASK_P1) {
+                // the parked tile is TP blocks of W x W words; block kb goes to W[slot][kb][16 tile .. ][.]
                 const uint32_t src = smem_u32(bufs + (size_t)b * kTileWords);
-                uint32_t* dst = ws + ((size_t)d.slot << 20) + (size_t)d.tile * 256;
+                uint32_t* dst = ws + ((size_t)d.slot << 20) + (size_t)d.tile * (W * W);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < (int)TP / 32; ++h) {
                     const int kb = lane + 32 * h;
-                    bulk_s2g(dst + (size_t)kb * 16384, src + kb * 1024, 1024);
+                    bulk_s2g(dst + (size_t)kb * (1024 * W), src + kb * (W * W * 4), W * W * 4);
                 }
                 bulk_commit();
                 bulk_wait_all();
@@ -255,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         return;
     }
 
-    if (tid >= kComputeThreads) {
+    if (tid >= C::kComputeThreads) {
         // ================================================================== load warp
         const int lane = tid & 31;
         for (unsigned it = 0;; ++it) {
@@ -273,27 +265,30 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             int type;
             unsigned transform;
-            decode_block(ticket / kTilesPerPass, batch, type, transform);
-            const int tile = (int)(ticket % kTilesPerPass);
+            decode_block(ticket / TP, batch, lag, type, transform);
+            const int tile = (int)(ticket % TP);
             const unsigned slot = transform % ring;
             if (lane == 0) {
                 if (type == TASK_P1) {
-                    if (transform >= ring) wait_counter(&cnt2[transform - ring], kTilesPerPass, err, 0x40u);
+                    if (transform >= ring) wait_counter(&cnt2[transform - ring], TP, err, 0x40u);
                 } else {
-                    wait_counter(&cnt1[transform], kTilesPerPass, err, 0x41u);
+                    wait_counter(&cnt1[transform], TP, err, 0x41u);
                     fence_proxy_async();  // the intermediate was written through the async proxy of other SMs
                 }
                 desc[b] = Desc{type, tile, transform, slot};
+                __threadfence_block();
             }
             __syncwarp();
             const uint32_t dst = smem_u32(bufs + (size_t)b * kTileWords);
             if (type == TASK_P1) {
-                // rows j = (lane >> 2) + 8 i, 16-byte part lane & 3: 128 gathers per lane, immediate offsets only
-                const uint32_t* src = x + ((size_t)transform << 20) + (size_t)tile * 16 + (size_t)(lane >> 2) * 1024 +
-                                      (lane & 3) * 4;
-                const uint32_t d0 = dst + (uint32_t)(((lane >> 2) * 16 + (lane & 3) * 4) * 4);
+                // 16-byte gathers: W/4 per row of the tile, 8 W per lane, immediate offsets only
+                constexpr int PARTS = W / 4, ROWS_PER_IT = 32 / PARTS;
+                const int row0 = lane / PARTS, part = lane % PARTS;
+                const uint32_t* src = x + ((size_t)transform << 20) + (size_t)tile * W + (size_t)row0 * 1024 + part * 4;
+                const uint32_t d0 = dst + (uint32_t)((row0 * W + part * 4) * 4);
 #pragma unroll 16
-                for (int i = 0; i < 128; ++i) cp_async_16(d0 + (uint32_t)i * 512u, src + (size_t)i * 8192);
+                for (int i = 0; i < 8 * W; ++i)
+                    cp_async_16(d0 + (uint32_t)i * (ROWS_PER_IT * W * 4), src + (size_t)i * (ROWS_PER_IT * 1024));
                 cp_async_mbar_arrive_noinc(&full[b]);
             } else {
                 if (lane == 0) {
@@ -309,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 
     // ====================================================================== compute warps
-    const int w = tid & 15, t = tid >> 4;  // t = 0..31: sub-transform in round A, inner transform k1 in round B
+    const int w = tid % W, t = tid / W;  // t = 0..31: sub-transform in round A, inner transform k1 in round B
     for (unsigned it = 0;; ++it) {
         const int b = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
@@ -319,28 +314,28 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t* tile = bufs + (size_t)b * kTileWords;
         uint32_t v[32];
         if (d.type == TASK_P1) {
-            round_a<LAZY>(tile, t, w, w, md, rt, zt_s);
-            compute_barrier();
-            round_b_load(tile, t, w, v);
-            compute_barrier();  // every read of the tile is done: it becomes the parking area of the outputs
+            round_a<LAZY, W>(tile, t, w, w, md, rt, zt_s);
+            compute_barrier<C::kComputeThreads>();
+            round_b_load<W>(tile, t, w, v);
+            compute_barrier<C::kComputeThreads>();  // every read of the tile is done: it becomes the parking area
             radixR<LAZY, 5, true>(v, md, rt);
-            // k = t + 32 k0; multiply by scale * omega^(c k), c = 16 tile + w, park at [kb = k/16][w][k%16 ^ (w & 14)]
-            const uint2* twp = tw4 + (size_t)t * 1024 + (size_t)d.tile * 16 + w;
-            uint32_t* park = tile + (t >> 4) * 256 + w * 16 + ((t & 15) ^ (w & 14));
+            // k = t + 32 k0; multiply by scale * omega^(c k), c = W tile + w, park at [kb = k/W][w][k%W ^ f(w)]
+            const uint2* twp = tw4 + (size_t)t * 1024 + (size_t)d.tile * W + w;
+            uint32_t* park = tile + (t / W) * (W * W) + w * W + ((t % W) ^ C::f(w));
 #pragma unroll
             for (int k0 = 0; k0 < 32; ++k0) {
                 const uint2 tw = __ldg(twp + (size_t)k0 * 32768);
-                park[k0 * 512] = md.mul(v[k0], tw.x, tw.y);  // lazy: below 2p, which is all pass 2 needs
+                park[k0 * 32 * W] = md.mul(v[k0], tw.x, tw.y);  // lazy: below 2p, which is all pass 2 needs
             }
             fence_proxy_async_smem();  // generic-proxy writes of the tile before the store warp's bulk copies
             mbar_arrive(&staged[b]);
         } else {
-            round_a<LAZY>(tile, t, w ^ (t & 14), w, md, rt, zt_s);
-            compute_barrier();
-            round_b_load(tile, t, w, v);
+            round_a<LAZY, W>(tile, t, w ^ C::f(t % W), w, md, rt, zt_s);
+            compute_barrier<C::kComputeThreads>();
+            round_b_load<W>(tile, t, w, v);
             radixR<LAZY, 5, true>(v, md, rt);
-            // X[k + 1024 k2], k = 16 tile + w (this tile's rows), k2 = t + 32 k0
-            uint32_t* out = y + ((size_t)d.transform << 20) + (size_t)t * 1024 + (size_t)d.tile * 16 + w;
+            // X[k + 1024 k2], k = W tile + w (this tile's rows), k2 = t + 32 k0
+            uint32_t* out = y + ((size_t)d.transform << 20) + (size_t)t * 1024 + (size_t)d.tile * W + w;
 #pragma unroll
             for (int k0 = 0; k0 < 32; ++k0) __stcs(out + (size_t)k0 * 32768, md.canon(v[k0]));
             // the arrive releases these stores to the store warp at CTA scope; its single gpu-scope fence before the
@@ -352,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // bytes of workspace for `batch` transforms: ring + control block + two counters per transform
 static inline size_t workspace_bytes(size_t batch) {
-    const size_t ring = batch < kRing ? batch : kRing;
+    const size_t ring = batch < kRingMax ? batch : kRingMax;
     return (ring << 20) * sizeof(uint32_t) + sizeof(Ctrl) + 2 * batch * sizeof(unsigned int) + 64;
 }
 
