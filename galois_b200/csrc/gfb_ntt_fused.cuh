@@ -43,7 +43,36 @@ struct Cfg {
     static constexpr unsigned kTilesPerPass = 1024 / W;
     static constexpr int kTPerWarp = 32 / W;                // sub-transform indices t that share a warp
     static constexpr int kSigmaMask = kTPerWarp - 1;        // exchange swizzle: row (t ^ (k1 & mask))
-    static // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+    static constexpr size_t kSmemTiles = (size_t)kStages * kTileWords * sizeof(uint32_t);
+    static constexpr size_t kSmemBytes = kSmemTiles + 1024 * sizeof(uint2) + 256;
+    // column permutation inside a W x W block of the intermediate (keeps the parking stores conflict free)
+    static __device__ __forceinline__ int f(int w) { return W == 16 ? (w & 14) : (w & 4); }
+};
+// Pass 2 of transform T is queued `lag` transforms behind its pass 1, and the intermediate lives in a ring of `ring`
+// transforms.  Every CTA runs up to kStages tickets ahead of its compute warps, so a few hundred tickets are in flight:
+// the lag must cover that window or the load warps sit on the dependency counter, and the ring must cover lag + window
+// so pass 1 never waits for a slot.  GFB_NTT_LAG / GFB_NTT_RING override.
+constexpr unsigned kLagDefault = 5;
+constexpr unsigned kRingDefault = 12;
+constexpr unsigned kRingMax = 32;
+constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s at 1.9 GHz
+
+enum : int { TASK_P1 = 0, TASK_P2 = 1, TASK_DONE = 2 };
+
+struct Ctrl {  // device memory, zeroed before every launch; followed by cnt1[batch], cnt2[batch]
+    unsigned int ticket;
+    unsigned int error;
+    unsigned int pad[2];
+};
+
+struct Desc {
+    int type;
+    int tile;
+    unsigned transform;
+    unsigned slot;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -42,8 +42,9 @@ def main(tag):
              "Source: `scripts/profile_gpu.sh` under gpurun on one B200 (`--clock-control none`).  Durations under ncu are",
              "cold-cache and serialised: use them for shares and per-launch traffic, not as benchmark values.", ""]
     traffic = {}
-    workload_of = {"mul": "gfp_mul", "ntt": "ntt", "rs": "rs_decode", "gf128": "gf2_128_mul"}
-    for name in ("mul", "ntt", "rs", "gf128"):
+    workload_of = {"mul": "gfp_mul", "ntt": "ntt", "rs": "rs_decode", "gf128": "gf2_128_mul", "gf256": "gf256_mul",
+                   "ntt_fused": "ntt"}
+    for name in ("mul", "ntt", "ntt_fused", "rs", "gf256", "gf128"):
         fn = SRC / f"{tag}_{name}_raw.csv"
         if not fn.exists():
             continue
@@ -53,10 +54,13 @@ def main(tag):
             shutil.copy(det, DST / det.name)
         lines += [f"## {name}", "", "| kernel | time | dram read | dram write | regs | warps active % | issue active % | SM thr % | inst (warp) | smem bank conflicts / wavefronts |", "|---|---|---|---|---|---|---|---|---|---|"]
         tot = 0.0
-        units = {"mul": 10**8, "rs": 200000, "gf128": 10**7}.get(name)  # elements / codewords per captured launch
+        units = {"mul": 10**8, "rs": 200000, "gf128": 10**7, "gf256": 10**8}.get(name)  # elements / codewords per captured launch
         for d, u in raw_rows(fn):
-            if name == "ntt":
-                units = int(float(d["launch__grid_size"])) // 64  # one CTA per (transform, 16-wide tile): 64 per transform
+            if name in ("ntt", "ntt_fused"):
+                if "fused" in d["Kernel Name"]:
+                    units = 592  # the persistent kernel: one launch for the whole --batch 592 of the capture command
+                else:
+                    units = int(float(d["launch__grid_size"])) // 64  # one CTA per (transform, 16-wide tile)
             t = float(d["gpu__time_duration.sum"]) * UNIT[u["gpu__time_duration.sum"]]
             rd = float(d["dram__bytes_read.sum"]) * UNIT[u["dram__bytes_read.sum"]]
             wr = float(d["dram__bytes_write.sum"]) * UNIT[u["dram__bytes_write.sum"]]
