@@ -47,6 +47,9 @@ def load_reference():
     if str(REF_DIR) not in sys.path:
         sys.path.insert(0, str(REF_DIR))
     os.environ.setdefault("NUMBA_CACHE_DIR", str(ROOT / "baseline" / "_numba_cache"))
+    # the reference is single-threaded on this path except two prange loops (matmul_jit, evaluate_elementwise_jit); on a
+    # 128-core host Numba's default of one worker per core makes every tiny parallel region cost milliseconds
+    os.environ.setdefault("NUMBA_NUM_THREADS", "8")
     try:
         import warnings
 

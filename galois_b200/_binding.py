@@ -403,6 +403,12 @@ def _cuda_matmul(self, A, B, out=None, **kwargs):
     vi = _ref["verify_isinstance"]
     vi(A, self.field)
     vi(B, self.field)
+    if A.ndim < 1 or B.ndim < 1 or A.shape[-1] != (B.shape[-2] if B.ndim > 1 else B.shape[0]):
+        return NotImplemented  # let the reference raise its own error (NumPy's gufunc text for prime fields, _linalg.py:41-67)
+    try:
+        np.broadcast_shapes(A.shape[:-2], B.shape[:-2])
+    except ValueError:
+        return NotImplemented
     M = _mirror(self.field)
     C = _linalg.matmul(M, _to_m(M, A), _to_m(M, B))
     C = _to_ref(self.field, C) if isinstance(C, np.ndarray) and C.ndim else self.field(int(C), dtype=A.dtype)

@@ -21,7 +21,9 @@ constexpr int kTabThreads = 256;
 constexpr int kTabUnroll = 2;              // 128-bit vectors per operand in flight per thread
 constexpr size_t kTabBytes = 65536;
 
-// tab[0..65535] = a * b, tab[65536..] = a / b (0 where b == 0), index a << 8 | b
+// tab[0..65535] = a * b, tab[65536..] = a / b (0 where b == 0), index a << 8 | b;
+// tab[131072..] = a * b again at index (a << 8) | (b ^ ((a & 31) << 2)): rows start on different banks, for kernels whose
+// lanes hold different constant multipliers a and equal operands b (the decoder's Horner chains all start at b = 0)
 __global__ void k_build_tab8(BinaryLut f, uint8_t* tab) {
     extern __shared__ uint4 smem_raw[];
     f.init_smem(smem_raw);
@@ -34,6 +36,7 @@ __global__ void k_build_tab8(BinaryLut f, uint8_t* tab) {
     }
     tab[i] = prod;
     tab[kTabBytes + i] = quot;
+    tab[2 * kTabBytes + ((a << 8) | (b ^ ((a & 31u) << 2)))] = prod;
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,7 +181,7 @@ gfb_status ensure_tab8(gfb_field* f, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(mu);
     if (f->d_tab8) return GFB_OK;
     uint8_t* tab = nullptr;
-    GFB_CUDA_TRY(cudaMalloc((void**)&tab, 2 * kTabBytes));
+    GFB_CUDA_TRY(cudaMalloc((void**)&tab, 3 * kTabBytes));
     BinaryLut lut = f->bin_lut();
     k_build_tab8<<<256, 256, lut.smem_bytes(), st>>>(lut, tab);
     cudaError_t e = cudaGetLastError();

@@ -34,6 +34,7 @@ struct gfb_rs_code {
     uint8_t* d_exp8;            // 2*order entries
     uint8_t* d_log8;            // order entries
     uint8_t* d_logP;            // k x (n-k), 255 = zero entry
+    uint8_t* d_gen;             // generator polynomial, n-k+1 coefficients, degree-descending
 };
 
 namespace gfb {
@@ -48,6 +49,7 @@ struct RsDev {
     const uint8_t* exp8;
     const uint8_t* log8;
     const uint8_t* logP;
+    const uint8_t* gen;  // monic generator polynomial (degree-descending) or nullptr when the remainder route is off
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -455,6 +457,9 @@ static RsDev make_dev(const gfb_rs_code* rs) {
     d.exp8 = rs->d_exp8;
     d.log8 = rs->d_log8;
     d.logP = rs->d_logP;
+    // S_l = (r mod g)(alpha^(c+l)) needs g to be the true generator: always so for Reed-Solomon handles; the BCH handles the
+    // binding creates for decoding carry a placeholder polynomial, so binary BCH keeps the direct evaluation
+    d.gen = rs->base2 ? nullptr : rs->d_gen;
     return d;
 }
 
@@ -486,7 +491,7 @@ static gfb_status code_create(gfb_rs_code** out, gfb_field* f, int n, int k, int
     rs->base2 = base2;
     rs->q1 = q1;
     rs->log_alpha = f->h_log[alpha];
-    rs->d_exp8 = rs->d_log8 = rs->d_logP = nullptr;
+    rs->d_exp8 = rs->d_log8 = rs->d_logP = rs->d_gen = nullptr;
     HostGf gf{f->h_exp, f->h_log, q1};
     const int r = n - k;
     rs->gen.assign(gen, gen + r + 1);
@@ -519,6 +524,8 @@ static gfb_status code_create(gfb_rs_code** out, gfb_field* f, int n, int k, int
     if (e == cudaSuccess) e = cudaMemcpy(rs->d_exp8, exp8.data(), exp8.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(rs->d_log8, log8.data(), log8.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(rs->d_logP, logP.data(), logP.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->d_gen, rs->gen.size());
+    if (e == cudaSuccess) e = cudaMemcpy(rs->d_gen, rs->gen.data(), rs->gen.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_last_error("code_create upload", e);
         gfb_rs_destroy(rs);
@@ -575,6 +582,7 @@ void gfb_rs_destroy(gfb_rs_code* rs) {
     if (rs->d_exp8) cudaFree(rs->d_exp8);
     if (rs->d_log8) cudaFree(rs->d_log8);
     if (rs->d_logP) cudaFree(rs->d_logP);
+    if (rs->d_gen) cudaFree(rs->d_gen);
     delete rs;
 }
 
@@ -625,7 +633,7 @@ gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t
         const size_t cap = (size_t)sm_count() * 2;  // two 512-thread CTAs (64 KiB table each) per SM
         if (grid > cap) grid = cap;
         fastrs::k_rs_decode_fast<<<(unsigned)grid, fastrs::kThreadsPerCta, fastrs::kSmemBytes, (cudaStream_t)stream>>>(
-            d, rs->field->d_tab8, received, erasures, ns, decoded, (long long*)n_errors, N);
+            d, rs->field->d_tab8 + 2 * 65536, received, erasures, ns, decoded, (long long*)n_errors, N);
         GFB_CUDA_TRY(cudaGetLastError());
         return GFB_OK;
     }

@@ -9,8 +9,12 @@
 //     with one cp.async.bulk, shared by 16 warps): no LOG/EXP round trip, no zero tests (T[0][x] = 0);
 //   * polynomials live in registers, coefficient i in lane i (degree 32 terms in a warp-uniform register); shifts and
 //     broadcasts are warp shuffles;
-//   * syndromes: lane l runs Horner's rule for the root alpha^(c+l) as two independent chains (upper and lower half of
-//     the word) — 3 instructions per term: table load, broadcast load of the symbol, one LOP3 forming the next index;
+//   * syndromes: the received word is first reduced modulo the generator polynomial, rho = r mod g (an LFSR: lane j holds
+//     rho_j, per symbol one shuffle pair and ONE conflict-free load from the per-code table G[f][j] = f g_j), and the
+//     syndromes are S_l = rho(alpha^(c+l)) — 32-term Horner chains instead of 255-term ones (g(alpha^(c+l)) = 0).
+//     Codes with more than 32 parity symbols per 32 roots (binary BCH) keep the direct Horner evaluation;
+//   * the product table is stored with row a rotated by (a mod 32) banks, so lanes holding different constant
+//     multipliers and equal operands (every Horner chain starts at 0) hit different banks;
 //   * Berlekamp-Massey in the inversion-free form  C <- b C - d x^m B  (C stays a non-zero scalar multiple of the
 //     reference's connection polynomial: same L, same degree, same roots, and Forney's quotient Omega / Lambda' is scale
 //     invariant), branch-free apart from warp-uniform selects;
@@ -25,16 +29,20 @@ constexpr int kWarps = 16;
 constexpr int kThreadsPerCta = kWarps * 32;
 constexpr int kTab = 65536;
 constexpr int kRecStride = 256;
-constexpr size_t kSmemBytes = kTab + 512 + 256 + (size_t)kWarps * (kRecStride + 64 + 64);
+constexpr int kGTab = 256 * 32;  // G[f][j] = f * g_j for the remainder LFSR
+constexpr size_t kSmemBytes = kTab + kGTab + 512 + 256 + (size_t)kWarps * (kRecStride + 64 + 64);
 
 __device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// row offset of multiplier a in the bank-skewed product table: entry a * b sits at row(a) ^ b
+__device__ __forceinline__ uint32_t row(uint32_t a) { return (a << 8) ^ ((a & 31u) << 2); }
+
 struct Tables {
-    const uint8_t* T;    // product table, index a << 8 | b
+    const uint8_t* T;    // product table, a * b at row(a) ^ b
     const uint8_t* exp;  // alpha0^i, i < 2 q1 (alpha0 = the field's primitive element)
     const uint8_t* inv;  // multiplicative inverses, inv[0] = 0
     int q1;
-    __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) const { return T[(a << 8) | b]; }
+    __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) const { return T[row(a) ^ b]; }
     // alpha0^(la * x mod q1) for any integer x
     __device__ __forceinline__ uint32_t pow_alpha(int la, int x) const {
         int r = (int)(((long long)la * x) % q1);
@@ -61,7 +69,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     uint8_t* T = smem;
-    uint8_t* s_exp = smem + kTab;
+    uint8_t* G = smem + kTab;
+    uint8_t* s_exp = G + kGTab;
     uint8_t* s_inv = s_exp + 512;
     uint8_t* s_warp = s_inv + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,6 +104,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
     }
     const Tables gf{T, s_exp, s_inv, rs.q1};
     const int d1 = rs.d - 1;  // <= 32
+    const int R = rs.n - rs.k;                  // parity symbols = degree of g(x)
+    const bool lfsr = R <= 32 && rs.gen != nullptr;
+    if (lfsr) {
+        // G[f][j] = f * g_j, g_j = coefficient of x^j of the monic generator polynomial (rs.gen is degree-descending)
+        for (int i = threadIdx.x; i < kGTab; i += blockDim.x) {
+            const uint32_t f = i >> 5, j = i & 31;
+            G[i] = (int)j < R ? T[row(f) ^ rs.gen[R - j]] : 0;
+        }
+        __syncthreads();
+    }
     const int la = rs.log_alpha;
     const int q1 = rs.q1;
     const size_t warps_total = (size_t)gridDim.x * kWarps;
@@ -129,23 +148,38 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
         bool clean = false;
         uint32_t S = 0;
         if (!fail) {
-            // ---- syndromes S_l = r(alpha^(c+l)), l = lane < d1 (:1370): two Horner chains over the halves of the word
+            // ---- syndromes S_l = r(alpha^(c+l)), l = lane < d1 (:1370)
             const int lroot = (int)(((long long)la * (rs.c + lane)) % q1);  // log of the root alpha^(c + l)
-            const uint32_t xrow = (uint32_t)gf.exp[lroot] << 8;
-            const int h = ns >> 1;
-            uint32_t ia = xrow, ib = xrow;  // next table index of each chain (xrow | accumulator)
-            int i = ns - 1;
-            if (ns & 1) {
-                ia = xrow | rec[i];
-                --i;
+            const uint32_t xg = row(gf.exp[lroot]);
+            if (lfsr) {
+                // rho(x) = r(x) mod g(x): rho <- rho x + r_i (mod g), symbols in descending degree
+                uint32_t rho = 0;
+                const int top = R - 1;
+#pragma unroll 4
+                for (int i = ns - 1; i >= 0; --i) {
+                    const uint32_t f = __shfl_sync(0xffffffffu, rho, top);
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, rho, 1);
+                    rho = (lane == 0 ? (uint32_t)rec[i] : up) ^ (uint32_t)G[f * 32 + lane];
+                }
+                // S_l = rho(alpha^(c+l)): Horner over the R <= 32 coefficients
+                uint32_t acc = 0;
+                for (int j = top; j >= 0; --j) acc = (uint32_t)T[xg ^ acc] ^ __shfl_sync(0xffffffffu, rho, j);
+                S = acc;
+            } else {
+                // direct evaluation, two Horner chains over the halves of the word: r(x) = A(x) x^h + B(x)
+                const int h = ns >> 1;
+                uint32_t a = 0, bq = 0;
+                int i = ns - 1;
+                if (ns & 1) {
+                    a = rec[i];
+                    --i;
+                }
+                for (; i >= h; --i) {
+                    a = (uint32_t)T[xg ^ a] ^ rec[i];
+                    bq = (uint32_t)T[xg ^ bq] ^ rec[i - h];
+                }
+                S = gf.mul(a, gf.exp[(int)(((long long)lroot * h) % q1)]) ^ bq;
             }
-            // chain A walks i = ns-1 (or ns-2) .. h, chain B walks i - h .. 0
-            for (; i >= h; --i) {
-                ia = xrow | ((uint32_t)T[ia] ^ rec[i]);
-                ib = xrow | ((uint32_t)T[ib] ^ rec[i - h]);
-            }
-            const uint32_t A = ia & 255u, B = ib & 255u;
-            S = gf.mul(A, gf.exp[(int)(((long long)lroot * h) % q1)]) ^ B;  // r(x) = A(x) x^h + B(x)
             if (lane >= d1) S = 0;
             const uint32_t any = __ballot_sync(0xffffffffu, S != 0);
             if (any == 0 && u == 0) clean = true;  // :1373-1376
@@ -153,20 +187,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
         int v = 0, v_total = 0;
         if (!fail && !clean) {
             // ---- Gamma(x) = prod (1 - Y_k x) (:1389-1393): coefficient i in lane i, coefficient 32 in Gtop
-            uint32_t G = lane == 0 ? 1u : 0u, Gtop = 0;
+            uint32_t Gm = lane == 0 ? 1u : 0u, Gtop = 0;
             for (int k = 0; k < u; ++k) {
-                const uint32_t Yrow = gf.pow_alpha(la, (int)epos[k]) << 8;
-                const uint32_t g31 = __shfl_sync(0xffffffffu, G, 31);
-                Gtop ^= T[Yrow | g31];
-                G ^= T[Yrow | shift_up(G, 1, lane)];
+                const uint32_t Yrow = row(gf.pow_alpha(la, (int)epos[k]));
+                const uint32_t g31 = __shfl_sync(0xffffffffu, Gm, 31);
+                Gtop ^= T[Yrow ^ g31];
+                Gm ^= T[Yrow ^ shift_up(Gm, 1, lane)];
             }
             // ---- S'(x) = Gamma(x) S(x) mod x^(d-1) (:1408-1409)
             uint32_t Sp = S;
             if (u > 0) {
                 Sp = 0;
                 for (int i = 0; i <= u && i < 32; ++i) {
-                    const uint32_t g = __shfl_sync(0xffffffffu, G, i);
-                    Sp ^= T[(g << 8) | shift_up(S, i, lane)];
+                    const uint32_t g = __shfl_sync(0xffffffffu, Gm, i);
+                    Sp ^= T[row(g) ^ shift_up(S, i, lane)];
                 }
                 if (lane >= d1) Sp = 0;
             }
@@ -181,8 +215,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
                 const uint32_t s_new = __shfl_sync(0xffffffffu, Sp, (u + nn) & 31);
                 const uint32_t up = __shfl_up_sync(0xffffffffu, Sw, 1);
                 Sw = lane == 0 ? s_new : up;
-                const uint32_t dsc = warp_xor32(T[(C << 8) | Sw]);
-                const uint32_t Cnew = (uint32_t)T[(b << 8) | C] ^ (uint32_t)T[(dsc << 8) | Bs];
+                const uint32_t dsc = warp_xor32(T[row(C) ^ Sw]);
+                const uint32_t Cnew = (uint32_t)T[row(b) ^ C] ^ (uint32_t)T[row(dsc) ^ Bs];
                 const bool grow = dsc != 0 && 2 * L <= nn;
                 const uint32_t src = grow ? C : Bs;  // B <- old C (m = 1) or m += 1
                 if (dsc != 0) C = Cnew;
@@ -206,9 +240,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
                 if (u > 0) {
                     Lt = 0;
                     for (int i = 0; i <= u; ++i) {
-                        const uint32_t g = i < 32 ? __shfl_sync(0xffffffffu, G, i) : Gtop;
-                        if (i < 32) Lt ^= T[(g << 8) | shift_up(C, i, lane)];
-                        if (i >= 1) Lt_top ^= T[(g << 8) | __shfl_sync(0xffffffffu, C, (32 - i) & 31)];
+                        const uint32_t g = i < 32 ? __shfl_sync(0xffffffffu, Gm, i) : Gtop;
+                        if (i < 32) Lt ^= T[row(g) ^ shift_up(C, i, lane)];
+                        if (i >= 1) Lt_top ^= T[row(g) ^ __shfl_sync(0xffffffffu, C, (32 - i) & 31)];
                     }
                 }
                 const int lt_len = u + v + 1;
@@ -219,13 +253,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
                     const int i = lane + 32 * k;
                     int lx = (int)(((long long)la * i) % q1);
                     lx = lx ? q1 - lx : 0;
-                    xr[k] = (uint32_t)gf.exp[lx] << 8;
+                    xr[k] = row(gf.exp[lx]);
                     acc[k] = 0;
                 }
                 for (int j = lt_len - 1; j >= 0; --j) {
                     const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, Lt, j) : Lt_top;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = (uint32_t)T[xr[k] | acc[k]] ^ cj;
+                    for (int k = 0; k < 8; ++k) acc[k] = (uint32_t)T[xr[k] ^ acc[k]] ^ cj;
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -245,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
                     uint32_t Om = 0;
                     for (int i = 0; i <= v; ++i) {
                         const uint32_t li = __shfl_sync(0xffffffffu, C, i);
-                        Om ^= T[(li << 8) | shift_up(Sp, i, lane)];
+                        Om ^= T[row(li) ^ shift_up(Sp, i, lane)];
                     }
                     if (lane >= d1) Om = 0;
                     // ---- Forney (:1512-1556): lane r handles root r.  E = Omega'(X^-1) / Lambda_total'(X^-1) (X^-1)^(c-1);
@@ -253,12 +287,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2)
                     const int my = lane < v_total ? pos[lane] : 0;
                     int lx = (int)(((long long)la * my) % q1);
                     lx = lx ? q1 - lx : 0;
-                    const uint32_t xrow = (uint32_t)gf.exp[lx] << 8;
+                    const uint32_t xrow = row(gf.exp[lx]);
                     uint32_t num = 0, den = 0;
-                    for (int j = d1 - 1; j >= 0; --j) num = (uint32_t)T[xrow | num] ^ __shfl_sync(0xffffffffu, Om, j);
+                    for (int j = d1 - 1; j >= 0; --j) num = (uint32_t)T[xrow ^ num] ^ __shfl_sync(0xffffffffu, Om, j);
                     for (int j = lt_len - 1; j >= 1; --j) {
                         const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, Lt, j) : Lt_top;
-                        den = (uint32_t)T[xrow | den] ^ ((j & 1) ? cj : 0u);
+                        den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? cj : 0u);
                     }
                     if (lane < v_total) {
                         uint32_t E = 0;

@@ -18,6 +18,9 @@ def import_reference():
     if str(REF_DIR) not in sys.path:
         sys.path.insert(0, str(REF_DIR))
     os.environ.setdefault("NUMBA_CACHE_DIR", str(REF_DIR.parent / "_numba_cache"))
+    # two of the reference's kernels use prange (matmul_jit, evaluate_elementwise_jit, called once per Chien position
+    # by the decoder): with Numba's default of one worker per core a 128-core host spends milliseconds per tiny region
+    os.environ.setdefault("NUMBA_NUM_THREADS", "8")
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
