@@ -496,8 +496,8 @@ def _decode_code(ext_field, base_is_gf2: bool, n: int, alpha: int, c: int, n_roo
             d = n_roots + 1
             k = n - n_roots
             if base_is_gf2:
-                gen = np.zeros(d, dtype=np.uint8)  # the decoder never touches g(x): x^(n-k) keeps the constructor happy
-                gen[0] = 1
+                gen = np.zeros(d, dtype=np.uint8)  # the decoder never touches g(x): x^(n-k) + 1 keeps the constructor happy
+                gen[0] = gen[-1] = 1
                 st = lib.gfb_bch_create(ctypes.byref(out), h, n, k, d, c, ctypes.c_uint64(alpha), gen.ctypes.data)
             else:
                 st = lib.gfb_rs_create(ctypes.byref(out), h, n, k, c, ctypes.c_uint64(alpha))
