@@ -111,6 +111,49 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_encode(RsDev rs, const uint8_
     }
 }
 
+// Systematic encode as the generator polynomial's LFSR, for codes with at most 32 parity symbols: parity(x) =
+// m(x) x^R mod g(x) — the same [I | P] codeword the reference builds with `message @ P` (_linear.py:270-284; P's rows are
+// x^(R+i) mod g(x), _cyclic.py:206-217).  Lane j holds remainder coefficient j; per message symbol one broadcast of the top
+// coefficient, one shift and ONE conflict-free shared-memory load from G[f][j] = f g_j (consecutive bytes for consecutive
+// lanes) — against R log-domain lookups per symbol and lane in k_rs_encode.
+__global__ void __launch_bounds__(kRsThreads) k_rs_encode_lfsr(RsDev rs, const uint8_t* __restrict__ msg, int ks,
+                                                                uint8_t* __restrict__ cw, size_t N) {
+    __shared__ uint8_t G[256 * 32];
+    const int R = rs.n - rs.k;
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+        const int f = i >> 5, j = i & 31;
+        uint8_t v = 0;
+        if (j < R && f > 0 && f < rs.order) {
+            const uint8_t g = rs.gen[R - j];  // coefficient of x^j (gen is degree-descending)
+            if (g) v = rs.exp8[(int)rs.log8[f] + (int)rs.log8[g]];
+        }
+        G[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ns = ks + R;
+    const int top = R - 1;
+    const size_t warps_total = (size_t)gridDim.x * kRsWarps;
+    for (size_t cwi = (size_t)blockIdx.x * kRsWarps + warp; cwi < N; cwi += warps_total) {
+        const uint8_t* mrow = msg + cwi * ks;
+        uint8_t* crow = cw + cwi * ns;
+        uint32_t rho = 0;
+        for (int base = 0; base < ks; base += 32) {
+            const int i = base + lane;
+            const uint32_t mine = i < ks ? mrow[i] : 0u;  // 32 message symbols per pass, highest degree first
+            if (i < ks) crow[i] = (uint8_t)mine;
+            const int cnt = ks - base < 32 ? ks - base : 32;
+            for (int t = 0; t < cnt; ++t) {
+                const uint32_t f = __shfl_sync(0xffffffffu, mine, t) ^ __shfl_sync(0xffffffffu, rho, top);
+                const uint32_t up = __shfl_up_sync(0xffffffffu, rho, 1);
+                rho = (lane == 0 ? 0u : up) ^ (uint32_t)G[f * 32 + lane];
+            }
+        }
+        // parity symbol p (0 = first after the message) is the coefficient of x^(R-1-p)
+        if (lane < R) crow[ks + (R - 1 - lane)] = (uint8_t)rho;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
@@ -605,6 +648,16 @@ gfb_status gfb_rs_encode(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* c
     if (N == 0) return GFB_OK;
     RsDev d = make_dev(rs);
     const int r = rs->n - rs->k;
+    static const bool lfsr_on = [] {
+        const char* e = getenv("GFB_RS_ENCODE_LFSR");
+        return !(e && e[0] == '0');
+    }();
+    if (lfsr_on && r >= 1 && r <= 32 && rs->d_gen) {
+        d.gen = rs->d_gen;  // the true generator for every handle that encodes (RS and BCH alike)
+        k_rs_encode_lfsr<<<rs_grid(N), kRsThreads, 0, (cudaStream_t)stream>>>(d, msg, ks, cw, N);
+        GFB_CUDA_TRY(cudaGetLastError());
+        return GFB_OK;
+    }
     const size_t smem = 3 * (size_t)d.order + (size_t)rs->k * r + (size_t)kRsWarps * kMaxN;
     GFB_CUDA_TRY(cudaFuncSetAttribute(k_rs_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_rs_encode<<<rs_grid(N), kRsThreads, smem, (cudaStream_t)stream>>>(d, msg, ks, cw, N);
