@@ -909,6 +909,7 @@ class BchDecode(RsDecode):
     cpu_sample = "250 codewords per thread with 18 bit errors each (bch_decode_jit restatement, field GF(2), extension GF(2^8))"
 
 
+RsEncode.secondary_roofline = None
 RsEncode.ref_setup = None  # no galois-driven leg for these two (oracle port only)
 BchDecode.ref_setup = None
 WORKLOADS.update({"rs_decode_erasures": RsDecodeErasures, "rs_encode": RsEncode, "intt": Intt, "bch_decode": BchDecode})
@@ -1170,7 +1171,7 @@ class Convolve:
 
     def ref_setup(self, galois):
         GF = galois.GF(self.field_order)
-        self.ra, self.rb = GF(np.asarray(self.ha)), GF(np.asarray(self.hb))
+        self.ra, self.rb = GF.Random(self.na, seed=41), GF.Random(self.nb, seed=42)
 
     def ref_step(self):
         self.rz = np.convolve(self.ra, self.rb)
@@ -1180,9 +1181,13 @@ class Convolve:
 
     def cpu_step(self, threads):
         if not hasattr(self, "ca"):
-            self.ca = np.asarray(self.ha).astype(np.int64)
-            self.cb = np.asarray(self.hb).astype(np.int64)
-        self._oracle().convolve(self.ca, self.cb)
+            rng = np.random.default_rng(41)
+            self.ca = rng.integers(0, self.field_order, self.na, dtype=np.int64)
+            self.cb = rng.integers(0, self.field_order, self.nb, dtype=np.int64)
+            import oracle
+
+            self.cF = oracle.Field.prime(self.field_order) if self.field_order == P_NTT else oracle.Field.binary(8, 0x11D, alpha=2)
+        self.cF.convolve(self.ca, self.cb)
         return 1
 
     cpu_sample = "the same 4096 x 4096 convolution, schoolbook, one thread (convolve_jit's fall-back loop)"
@@ -1338,10 +1343,10 @@ class NttSharded:
         F = oracle.Field.prime(P_NTT)
         if not hasattr(self, "cx"):
             self.cN = 1 << 22
+            self.comega = pow(3, (P_NTT - 1) // self.cN, P_NTT)  # 3 is the smallest primitive root of 998244353
             self.cx = np.random.default_rng(3).integers(0, P_NTT, self.cN, dtype=np.int64)
-            self.comega = int(self.GF.primitive_root_of_unity(self.cN))
         F.fft(self.cx, self.comega)
-        return self.cN / self.N  # fraction of a 2^26-point transform by element count (log factor ignored: 22 vs 26 stages)
+        return self.cN / (1 << self.LOG_N)  # fraction of a 2^26-point transform by element count (log factor ignored: 22 vs 26 stages)
 
     cpu_sample = "one 2^22-point transform (1/16 of the elements), one thread, counted as 1/16 transform"
     cpu_cores = 1
@@ -1569,7 +1574,8 @@ def main():
     # dominant kernel: algorithmic bytes of one step on this rank / mean device time of one step
     achieved = work.units_per_step * cls.bytes_per_unit / (ms / 1e3 / args.steps) / 1e9
 
-    sec_roofline = work.secondary_roofline(work.units_per_step * args.steps / (ms / 1e3)) if hasattr(work, "secondary_roofline") else None
+    sec_roofline = (work.secondary_roofline(work.units_per_step * args.steps / (ms / 1e3))
+                    if callable(getattr(work, "secondary_roofline", None)) else None)
 
     # ---- end to end through the reference-facing API with HOST buffers (same metric): the reference's own classes
     #      with galois_b200.enable() when baseline/_ref is importable, else the mirror classes
@@ -1624,7 +1630,7 @@ def main():
                                "units_per_gpu_per_step": w.units_per_step,
                                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                             "kernel": ecls.kernel, "algorithmic_bytes_per_unit": ecls.bytes_per_unit}}
-                if hasattr(w, "secondary_roofline"):
+                if callable(getattr(w, "secondary_roofline", None)):
                     extras[key]["roofline_secondary"] = w.secondary_roofline(w.units_per_step * esteps / (ems / 1e3))
                 if world > 1 and ecls.scaling == "strong":
                     extras[key]["final_gather_ms"] = time_gather(w, world)
