@@ -27,6 +27,17 @@ struct CheapInv<BinaryLut> {
     static constexpr bool value = true;
 };
 
+// 128-bit vectors per thread in the kernels that carry a Montgomery batch inversion (INV, DIV).  One field inverse
+// (Fermat: ~60 multiplies for a 31-bit prime; Itoh-Tsujii: ~135 carry-less multiplies for GF(2^128)) is shared by all the
+// elements a thread holds, so the kernels stop being inverse-bound once a thread holds ~32 word-size elements (8 of the
+// 16-byte ones: 4 registers each).  Round 1 held 8: the inverse was 60 of ~100 instructions per element.
+template <typename T, typename F, int VEC>
+struct InvUnroll {
+    static constexpr int wanted = sizeof(T) == 16 ? kUnrollDefault : 32 / VEC;  // 16-byte elements: deeper batches spill (clmul is register-hungry)
+    static constexpr int value = (CheapInv<F>::value || VEC * sizeof(T) != 16) ? kUnrollDefault
+                                 : (wanted > kUnrollDefault ? wanted : kUnrollDefault);
+};
+
 // Montgomery batch inversion of K elements held in registers.  Zero inputs set `zero_seen`
 // and produce 0 (the reference raises ZeroDivisionError; the caller reports the flag).
 template <typename F, int K>
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, OP == GFB_DIV ? 1 : UnrollFor<T>::mi
         }
     }
     // division carries a batch inversion: keep 4 vectors per thread there to amortise the field inverse
-    constexpr int kUnroll = (OP == GFB_DIV) ? kUnrollDefault : UnrollFor<T>::value;
+    constexpr int kUnroll = (OP == GFB_DIV) ? InvUnroll<T, F, VEC>::value : UnrollFor<T>::value;
     const size_t nvec = n / VEC;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, OP == GFB_INV ? 1 : UnrollFor<T>::mi
     f.init_smem(smem_raw);
     bool zero_seen = false;
     // inversion amortises one field inverse over the K elements a thread holds: keep 4 vectors there
-    constexpr int kUnroll = (OP == GFB_INV) ? kUnrollDefault : UnrollFor<T>::value;
+    constexpr int kUnroll = (OP == GFB_INV) ? InvUnroll<T, F, VEC>::value : UnrollFor<T>::value;
     const size_t nvec = n / VEC;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
