@@ -1282,13 +1282,15 @@ class MatmulRs:
 
 
 class NttSharded:
-    """SURVEY.md §8f rank 3 (second half): ONE 2^26-point NTT over GF(998244353) spread over the ranks — local column pass,
-    NCCL all-to-all, local row pass (galois_b200._dist.ShardedNtt).  The only workload whose curve a collective can limit;
-    `phases_ms` names the all-to-all's share."""
+    """SURVEY.md §8f rank 3 (second half): ONE 2^26-point NTT spread over the ranks — local column pass, NCCL all-to-all,
+    local row pass (galois_b200._dist.ShardedNtt).  Over GF(2013265921) = GF(15 * 2^27 + 1): 998244353 - 1 = 2^23 * 7 * 17
+    has no 2^26-th roots of unity.  The only workload whose curve a collective can limit; `phases_ms` names the all-to-all's
+    share."""
 
     metric, unit, dtype, scaling = "ntt_2p26_sharded_per_sec", "NTT/s", "uint32", "strong"
     kernel = "k_ntt_* (column pass) -> all_to_all_single (NCCL) -> k_ntt_* (row pass)"
     LOG_N = 26
+    P = 2013265921  # 15 * 2^27 + 1, smallest primitive root 31
     bytes_per_unit = 2 * 4 * 2**26
 
     def __init__(self, rank, world, batch=None):
@@ -1298,14 +1300,14 @@ class NttSharded:
         from galois_b200._dist import ShardedNtt
 
         self.gb, self.torch = gb, torch
-        self.GF = gb.GF(P_NTT)
+        self.GF = gb.GF(self.P)
         self.N = 1 << self.LOG_N
         self.sh = ShardedNtt(self.GF, self.N)
-        self.name = f"one 2^{self.LOG_N}-point NTT over GF(998244353) sharded over {world} GPU(s) (column slabs in, row slabs out)"
+        self.name = f"one 2^{self.LOG_N}-point NTT over GF({self.P}) sharded over {world} GPU(s) (column slabs in, row slabs out)"
         # two impulses: X[k] = w^(j0 k) + 5 w^(j1 k) checks every index map and twiddle at full size
         self.j0, self.j1 = 12345677 % self.N, (3 * self.N // 7) | 1
         g = torch.Generator(device="cuda").manual_seed(17)
-        slab = torch.randint(0, P_NTT, (self.sh.n1, self.sh.cols), dtype=torch.int32, device="cuda", generator=g)
+        slab = torch.randint(0, self.P, (self.sh.n1, self.sh.cols), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
         self.x = gb.DeviceArray(self.GF, slab.view(torch.uint8).reshape(-1), (self.sh.n1, self.sh.cols), np.uint32)
         self.units_per_step = 1 if rank == 0 else 0  # one transform for the whole job
         type(self).bytes_per_unit = 2 * 4 * self.N // world  # per-GPU share of the compulsory traffic (roofline is per GPU)
@@ -1318,7 +1320,7 @@ class NttSharded:
         self.phases.append(dict(self.sh.timings))
 
     def check(self):
-        torch, sh, p = self.torch, self.sh, P_NTT
+        torch, sh, p = self.torch, self.sh, self.P
         imp = torch.zeros((sh.n1, sh.n2), dtype=torch.int32, device="cuda")
         imp.view(-1)[self.j0] = 1
         imp.view(-1)[self.j1] = 5
@@ -1330,7 +1332,8 @@ class NttSharded:
         ks = idx.reshape(-1)[sel].cpu().numpy().astype(object)
         w = sh.omega
         want = [(pow(w, int(self.j0 * k % self.N), p) + 5 * pow(w, int(self.j1 * k % self.N), p)) % p for k in ks]
-        assert got.reshape(-1)[sel].cpu().numpy().astype(np.int64).tolist() == want, "sharded NTT differs from w^(jk)"
+        have = (got.reshape(-1)[sel].cpu().numpy().astype(np.int64) & 0xFFFFFFFF).tolist()
+        assert have == want, "sharded NTT differs from w^(jk)"
 
     def e2e_setup(self, galois=None):
         self.e2e_units = None
@@ -1340,11 +1343,11 @@ class NttSharded:
     def cpu_step(self, threads):
         import oracle
 
-        F = oracle.Field.prime(P_NTT)
+        F = oracle.Field.prime(self.P)
         if not hasattr(self, "cx"):
             self.cN = 1 << 22
-            self.comega = pow(3, (P_NTT - 1) // self.cN, P_NTT)  # 3 is the smallest primitive root of 998244353
-            self.cx = np.random.default_rng(3).integers(0, P_NTT, self.cN, dtype=np.int64)
+            self.comega = pow(31, (self.P - 1) // self.cN, self.P)  # 31 is the smallest primitive root of 2013265921
+            self.cx = np.random.default_rng(3).integers(0, self.P, self.cN, dtype=np.int64)
         F.fft(self.cx, self.comega)
         return self.cN / (1 << self.LOG_N)  # fraction of a 2^26-point transform by element count (log factor ignored: 22 vs 26 stages)
 

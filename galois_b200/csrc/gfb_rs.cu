@@ -648,9 +648,12 @@ gfb_status gfb_rs_encode(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* c
     if (N == 0) return GFB_OK;
     RsDev d = make_dev(rs);
     const int r = rs->n - rs->k;
+    // GFB_RS_ENCODE_LFSR=1 selects the generator-LFSR encoder.  Measured on a B200 (1e6 RS(255,223) messages): 2.72e8 cw/s
+    // against 2.99e8 for k_rs_encode — one conflict-free load per symbol instead of 32 lookups, but the 223 steps form one
+    // dependent shuffle -> load -> xor chain per codeword, so it is latency-bound; the lookup kernel stays the default.
     static const bool lfsr_on = [] {
         const char* e = getenv("GFB_RS_ENCODE_LFSR");
-        return !(e && e[0] == '0');
+        return e && e[0] == '1';
     }();
     if (lfsr_on && r >= 1 && r <= 32 && rs->d_gen) {
         d.gen = rs->d_gen;  // the true generator for every handle that encodes (RS and BCH alike)

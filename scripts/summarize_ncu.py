@@ -44,7 +44,7 @@ def main(tag):
     traffic = {}
     workload_of = {"mul": "gfp_mul", "ntt": "ntt", "rs": "rs_decode", "gf128": "gf2_128_mul", "gf256": "gf256_mul",
                    "ntt_fused": "ntt"}
-    for name in ("mul", "ntt", "ntt_fused", "rs", "gf256", "gf128"):
+    for name in ("mul", "ntt", "rs", "gf256", "gf128"):
         fn = SRC / f"{tag}_{name}_raw.csv"
         if not fn.exists():
             continue
