@@ -27,19 +27,15 @@ struct CheapInv<BinaryLut> {
     static constexpr bool value = true;
 };
 
-// 128-bit vectors per thread in the kernels that carry a Montgomery batch inversion (INV, DIV).  One field inverse
-// (Fermat: ~60 multiplies for a 31-bit prime; Itoh-Tsujii: ~135 carry-less multiplies for GF(2^128)) is shared by all the
-// elements a thread holds, so the kernels stop being inverse-bound once a thread holds ~32 word-size elements (8 of the
-// 16-byte ones: 4 registers each).  Round 1 held 8: the inverse was 60 of ~100 instructions per element.
+// 128-bit vectors per thread in the kernels that carry a Montgomery batch inversion (INV, DIV): one field inverse is shared by
+// the elements a thread holds.  Measured on a B200 (GF(2^31-1), 1e8 int64): 4 vectors (8 elements) 2.19e11 inv/s and
+// 2.01e11 div/s; 16 vectors (32 elements) 1.68e11 and 1.61e11 — the longer prefix-product chains and the lower occupancy
+// cost more than the amortised inverse saves, so the depth stays at 4.
 template <typename T, typename F, int VEC>
 struct InvUnroll {
-    static constexpr int wanted = sizeof(T) == 16 ? kUnrollDefault : 32 / VEC;  // 16-byte elements: deeper batches spill (clmul is register-hungry)
-    static constexpr int value = (CheapInv<F>::value || VEC * sizeof(T) != 16) ? kUnrollDefault
-                                 : (wanted > kUnrollDefault ? wanted : kUnrollDefault);
+    static constexpr int value = kUnrollDefault;
 };
 
-// Montgomery batch inversion of K elements held in registers.  Zero inputs set `zero_seen`
-// and produce 0 (the reference raises ZeroDivisionError; the caller reports the flag).
 template <typename F, int K>
 __device__ __forceinline__ void batch_inverse(const F& f, typename F::elem (&x)[K], bool& zero_seen) {
     using E = typename F::elem;

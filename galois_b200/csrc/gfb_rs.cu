@@ -23,6 +23,10 @@
 #include "gfb_ewise_api.cuh"
 #include "gfb_host.cuh"
 
+#ifndef GFB_RS_DEFAULT_DECODER
+#define GFB_RS_DEFAULT_DECODER 0  // 0 = log-domain warp-per-codeword, 1 = product-table, 2 = bit-sliced
+#endif
+
 struct gfb_rs_code {
     gfb_field* field;
     int n, k, d, c, m;  // d = design distance: d - 1 consecutive roots alpha^c .. alpha^(c+d-2)
@@ -486,6 +490,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_decode(RsDev rs, const uint8_
 }
 
 #include "gfb_rs_fast.cuh"
+#include "gfb_rs_bs.cuh"
 
 static RsDev make_dev(const gfb_rs_code* rs) {
     RsDev d;
@@ -675,14 +680,36 @@ gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t
     if (ns < rs->n - rs->k + 1 || ns > rs->n) return GFB_ERR_BAD_ARG;
     if (N == 0) return GFB_OK;
     RsDev d = make_dev(rs);
+    // decoder selection for codes with at most 32 parity symbols: GFB_RS_DECODER = "bs" (bit-sliced, 32 codewords per
+    // warp, gfb_rs_bs.cuh), "fast" (register-resident, product table, gfb_rs_fast.cuh) or "log" (k_rs_decode below)
+    static const int decoder = [] {
+        const char* e = getenv("GFB_RS_DECODER");
+        if (e && !strcmp(e, "bs")) return 2;
+        if (e && !strcmp(e, "fast")) return 1;
+        if (e && !strcmp(e, "log")) return 0;
+        return GFB_RS_DEFAULT_DECODER;
+    }();
+    if (decoder == 2 && rs->d - 1 <= 32 && rs->d >= 2) {
+        gfb_status rc = ensure_tab8(rs->field, (cudaStream_t)stream);
+        if (rc != GFB_OK) return rc;
+        GFB_CUDA_TRY(cudaFuncSetAttribute(bsrs::k_rs_decode_bs, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)bsrs::kSmemBytes));
+        size_t grid = ((N + 31) / 32 + bsrs::kWarps - 1) / bsrs::kWarps;
+        const size_t cap = (size_t)sm_count();
+        if (grid > cap) grid = cap;
+        bsrs::k_rs_decode_bs<<<(unsigned)grid, bsrs::kThreadsPerCta, bsrs::kSmemBytes, (cudaStream_t)stream>>>(
+            d, rs->field->d_tab8 + 2 * 65536, received, erasures, ns, decoded, (long long*)n_errors, N);
+        GFB_CUDA_TRY(cudaGetLastError());
+        return GFB_OK;
+    }
     // GFB_RS_FAST=1 selects the register-resident decoder of gfb_rs_fast.cuh.  Measured on a B200 (1e6 RS(255,223) words x 16
     // errors): 1.14e8 cw/s against 1.21e8 for k_rs_decode below — it halves the instruction count but its product-table
     // lookups make it shared-memory-wavefront bound (ncu: 82 % of the cycles, 3.4-way conflicts on data-dependent byte
     // loads), so the log-domain kernel stays the default.
     static const bool fast_on = [] {
         const char* e = getenv("GFB_RS_FAST");
-        return e && e[0] == '1';
-    }();
+        return (e && e[0] == '1');
+    }() || decoder == 1;
     if (fast_on && rs->d - 1 <= 32 && rs->d >= 2) {
         // at most 32 parity symbols: the register-resident decoder on the field's product table (gfb_rs_fast.cuh)
         gfb_status rc = ensure_tab8(rs->field, (cudaStream_t)stream);

@@ -1,0 +1,378 @@
+// gfb_rs_bs.cuh — bit-sliced errors-and-erasures decoder: 32 codewords per warp, codes with at most 32 parity symbols over
+// GF(2^m), m <= 8 (included by gfb_rs.cu).
+//
+// Same algorithm and the same decisions as bch_decode_jit.implementation
+// (/root/reference/src/galois/_codes/_bch.py:1337-1578; Berlekamp-Massey _lfsr.py:1647-1702).  ncu on the two
+// warp-per-codeword decoders (profiles/r02_summary.md) showed where the time goes: ~12 k field multiply-adds per codeword sit
+// in the syndromes (d-1 Horner chains over n symbols) and the Chien search (n Horner chains over the locator), every one of
+// them a multiplication by a CONSTANT (a root alpha^(c+l), a position alpha^-i), and a table lookup per product costs either
+// ~7 instructions (log / antilog plumbing) or a 3.4-way bank-conflicted byte load.  A constant multiply over GF(2^m) is an
+// m x m bit matrix, so with the symbols of 32 codewords held as m bit-planes (bit k of plane j = bit j of codeword k's
+// symbol) one Horner step for 32 codewords is 64 LOP3 (`acc_b & mask_jb ^ ...`) and 8 broadcast loads — no tables, no
+// conflicts, 0.08 instructions per multiply-add.
+//   1. load: lane k reads codeword k's symbols (erasures zeroed); 8 warp ballots per position turn them into planes
+//      R[i][j] in shared memory; the received rows are copied to the output as they are;
+//   2. syndromes: lane l holds the 64 masks of alpha^(c+l) and runs Horner over the planes; the 8 result planes are
+//      transposed back to one byte per (codeword, syndrome);
+//   3. per codeword (warp-parallel over coefficients, products through the bank-skewed product table as in
+//      gfb_rs_fast.cuh): Gamma, S' = Gamma S, inversion-free Berlekamp-Massey, Lambda_total = Gamma Lambda, Omega' = Lambda S';
+//   4. Chien search: Lambda_total of the 32 codewords as planes; lane = position, 8 rounds of 32 positions, Horner with the
+//      masks of alpha^-i; a zero across the 8 result planes marks a root of codeword k in bit k;
+//   5. per codeword: root list from the bit masks, Forney, corrected symbols patched into the output row.
+// Decoder failures (more than d-1 erasures, 2v + u > d - 1, wrong root count) return -1 and leave the received row.
+#pragma once
+
+namespace bsrs {  // (inside namespace gfb)
+
+constexpr int kWarps = 12;
+constexpr int kThreadsPerCta = kWarps * 32;
+constexpr int kTab = 65536;
+constexpr int kOffPlanes = 0;                  // uint32 R[256][8]
+constexpr int kOffMask = 8192;                 // uint32 [256]: erasure mask per position, later root mask per position
+constexpr int kOffS = kOffMask + 1024;         // uint8 S[32][32], later Omega'[32][32]
+constexpr int kOffLt = kOffS + 1024;           // uint8 Lambda_total[32][36] (33 used)
+constexpr int kOffLP = kOffLt + 1152;          // uint32 LP[33][8]: coefficient planes for the Chien search
+constexpr int kOffMeta = kOffLP + 1056;        // int32 meta[32][4] (state, u, v, lt_len) + 128 bytes of position scratch
+constexpr int kWarpBytes = kOffMeta + 512 + 128;
+constexpr size_t kSmemBytes = kTab + 512 + 256 + (size_t)kWarps * kWarpBytes;
+static_assert(kSmemBytes <= 232448, "bit-sliced decoder exceeds the shared memory of an SM");
+
+enum : int { ST_FAIL = 0, ST_CLEAN = 1, ST_OK = 2 };
+
+using fastrs::row;
+using fastrs::shift_up;
+using fastrs::sm_addr;
+using fastrs::warp_xor32;
+
+// masks of the constant multiplier x: mk[j * 8 + b] = all-ones iff bit j of x * 2^b is set
+__device__ __forceinline__ void build_masks(const uint8_t* __restrict__ T, uint32_t x, uint32_t (&mk)[64]) {
+    const uint32_t xr = row(x);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t cb = T[xr ^ (1u << b)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mk[j * 8 + b] = 0u - ((cb >> j) & 1u);
+    }
+}
+
+// acc <- x * acc + add on 8 bit-planes (32 independent field elements)
+__device__ __forceinline__ void horner_step(const uint32_t (&mk)[64], uint32_t (&acc)[8], const uint32_t* __restrict__ add) {
+    uint32_t nw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t v = add[j];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) v ^= acc[b] & mk[j * 8 + b];
+        nw[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = nw[j];
+}
+
+__global__ void __launch_bounds__(kThreadsPerCta, 1)
+    k_rs_decode_bs(RsDev rs, const uint8_t* __restrict__ tab_g, const uint8_t* __restrict__ received,
+                   const uint8_t* __restrict__ erasures, int ns, uint8_t* __restrict__ decoded,
+                   long long* __restrict__ n_errors, size_t N) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    uint8_t* T = smem;
+    uint8_t* s_exp = smem + kTab;
+    uint8_t* s_inv = s_exp + 512;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* wbase = s_inv + 256 + (size_t)warp * kWarpBytes;
+    uint32_t* R = reinterpret_cast<uint32_t*>(wbase + kOffPlanes);
+    uint32_t* PM = reinterpret_cast<uint32_t*>(wbase + kOffMask);
+    uint8_t* Ss = wbase + kOffS;
+    uint8_t* LtS = wbase + kOffLt;
+    uint32_t* LP = reinterpret_cast<uint32_t*>(wbase + kOffLP);
+    int* meta = reinterpret_cast<int*>(wbase + kOffMeta);
+    uint8_t* scratch = wbase + kOffMeta + 512;  // 64 bytes erasure positions, 64 bytes root positions
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_addr(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(sm_addr(&bar)),
+                     "r"((uint32_t)kTab)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_addr(T)),
+                     "l"(tab_g), "r"((uint32_t)kTab), "r"(sm_addr(&bar))
+                     : "memory");
+    }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_exp[i] = i < 2 * rs.order ? rs.exp8[i] : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_inv[i] = (i > 0 && i < rs.order) ? rs.exp8[rs.q1 - rs.log8[i]] : 0;
+    __syncthreads();
+    {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(sm_addr(&bar))
+                : "memory");
+        }
+    }
+    const fastrs::Tables gf{T, s_exp, s_inv, rs.q1};
+    const int d1 = rs.d - 1;  // <= 32
+    const int la = rs.log_alpha;
+    const int q1 = rs.q1;
+    const size_t groups = (N + 31) / 32;
+    const size_t warps_total = (size_t)gridDim.x * kWarps;
+    uint32_t mk[64];
+
+    for (size_t grp = (size_t)blockIdx.x * kWarps + warp; grp < groups; grp += warps_total) {
+        const size_t cw0 = grp * 32;
+        const int ncw = (int)(N - cw0 < 32 ? N - cw0 : 32);
+        const bool mine = lane < ncw;
+        const uint8_t* rrow = received + (cw0 + lane) * ns;
+        const uint8_t* erow = erasures ? erasures + (cw0 + lane) * ns : nullptr;
+        __syncwarp();
+        // ---- 1. output = received (the rows of the group are contiguous); planes of the received symbols
+        {
+            const uint8_t* src = received + cw0 * ns;
+            uint8_t* dst = decoded + cw0 * ns;
+            const size_t bytes = (size_t)ncw * ns;
+            if ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+                const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+                for (size_t i = lane; i < bytes / 4; i += 32) d4[i] = s4[i];
+                for (size_t i = (bytes & ~(size_t)3) + lane; i < bytes; i += 32) dst[i] = src[i];
+            } else {
+                for (size_t i = lane; i < bytes; i += 32) dst[i] = src[i];
+            }
+        }
+        uint32_t any_era = 0;
+        for (int i = 0; i < ns; ++i) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
+            uint32_t b = 0, er = 0;
+            if (mine) {
+                b = rrow[ns - 1 - i];
+                er = erow ? (erow[ns - 1 - i] != 0) : 0u;
+            }
+            const uint32_t em = __ballot_sync(0xffffffffu, er);
+            if (er) b = 0;
+            any_era |= em;
+            uint32_t keep = em;  // lane 8 keeps the erasure mask, lanes 0..7 plane `lane`
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t pj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
+                if (lane == j) keep = pj;
+            }
+            if (lane < 8) R[i * 8 + lane] = keep;
+            if (lane == 8) PM[i] = keep;
+        }
+        __syncwarp();
+        // ---- 2. syndromes S_l = r(alpha^(c+l)), lane l, all 32 codewords at once (:1370)
+        {
+            build_masks(T, gf.pow_alpha(la, rs.c + lane), mk);
+            uint32_t acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0;
+            for (int i = ns - 1; i >= 0; --i) horner_step(mk, acc, R + i * 8);
+            for (int k = 0; k < 32; ++k) {
+                uint32_t byte = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) byte |= ((acc[j] >> k) & 1u) << j;
+                Ss[k * 32 + lane] = lane < d1 ? (uint8_t)byte : 0;
+            }
+        }
+        __syncwarp();
+        // ---- 3. per codeword: Gamma, S', Berlekamp-Massey, Lambda_total, Omega'
+        int max_len = 0;
+        for (int k = 0; k < ncw; ++k) {
+            const uint32_t S = Ss[k * 32 + lane];
+            // erasure positions of codeword k, ascending
+            int u = 0;
+            if (any_era) {
+#pragma unroll 1
+                for (int r = 0; r < 8; ++r) {
+                    const int i = lane + 32 * r;
+                    const uint32_t er = (i < ns) ? ((PM[i] >> k) & 1u) : 0u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, er);
+                    if (er) {
+                        const int slot = u + __popc(bal & ((1u << lane) - 1u));
+                        if (slot < 64) scratch[slot] = (uint8_t)i;
+                    }
+                    u += __popc(bal);
+                }
+                __syncwarp();
+            }
+            int state = ST_OK, v = 0, lt_len = 1;
+            uint32_t Lt = 0, Lt_top = 0, Om = 0;
+            if (u > d1) {  // :1357-1360
+                state = ST_FAIL;
+            } else if (__ballot_sync(0xffffffffu, S != 0) == 0 && u == 0) {
+                state = ST_CLEAN;  // :1373-1376
+            } else {
+                // Gamma(x) = prod (1 - Y_k x) (:1389-1393): coefficient i in lane i, coefficient 32 in Gtop
+                uint32_t Gm = lane == 0 ? 1u : 0u, Gtop = 0;
+                for (int e = 0; e < u; ++e) {
+                    const uint32_t Yrow = row(gf.pow_alpha(la, (int)scratch[e]));
+                    const uint32_t g31 = __shfl_sync(0xffffffffu, Gm, 31);
+                    Gtop ^= T[Yrow ^ g31];
+                    Gm ^= T[Yrow ^ shift_up(Gm, 1, lane)];
+                }
+                // S'(x) = Gamma(x) S(x) mod x^(d-1) (:1408-1409)
+                uint32_t Sp = S;
+                if (u > 0) {
+                    Sp = 0;
+                    for (int i = 0; i <= u && i < 32; ++i) {
+                        const uint32_t g = __shfl_sync(0xffffffffu, Gm, i);
+                        Sp ^= T[row(g) ^ shift_up(S, i, lane)];
+                    }
+                    if (lane >= d1) Sp = 0;
+                }
+                // Berlekamp-Massey on S'[u:], inversion-free (:1421-1428, _lfsr.py:1647-1702)
+                uint32_t C = lane == 0 ? 1u : 0u, Bs = lane == 1 ? 1u : 0u, Sw = 0, b = 1;
+                int L = 0;
+                const int ls = d1 - u;
+                for (int nn = 0; nn < ls; ++nn) {
+                    const uint32_t s_new = __shfl_sync(0xffffffffu, Sp, (u + nn) & 31);
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, Sw, 1);
+                    Sw = lane == 0 ? s_new : up;
+                    const uint32_t dsc = warp_xor32(T[row(C) ^ Sw]);
+                    const uint32_t Cnew = (uint32_t)T[row(b) ^ C] ^ (uint32_t)T[row(dsc) ^ Bs];
+                    const bool grow = dsc != 0 && 2 * L <= nn;
+                    const uint32_t src = grow ? C : Bs;
+                    if (dsc != 0) C = Cnew;
+                    if (grow) {
+                        L = nn + 1 - L;
+                        b = dsc;
+                    }
+                    Bs = shift_up(src, 1, lane);
+                }
+                const int len = L + 1 < ls ? L + 1 : ls;
+                const uint32_t nzmask = __ballot_sync(0xffffffffu, lane < len && C != 0);
+                const int lam_len = nzmask ? 32 - __clz(nzmask) : 1;
+                if (lane >= lam_len) C = 0;
+                if (u >= d1) C = lane == 0 ? 1u : 0u;
+                v = (u < d1 ? lam_len : 1) - 1;
+                if (2 * v + u > d1) {  // :1431-1433
+                    state = ST_FAIL;
+                } else {
+                    // Lambda_total = Gamma Lambda (:1449)
+                    Lt = C;
+                    if (u > 0) {
+                        Lt = 0;
+                        for (int i = 0; i <= u; ++i) {
+                            const uint32_t g = i < 32 ? __shfl_sync(0xffffffffu, Gm, i) : Gtop;
+                            if (i < 32) Lt ^= T[row(g) ^ shift_up(C, i, lane)];
+                            if (i >= 1) Lt_top ^= T[row(g) ^ __shfl_sync(0xffffffffu, C, (32 - i) & 31)];
+                        }
+                    }
+                    lt_len = u + v + 1;
+                    // Omega' = Lambda S' mod x^(d-1) (:1498-1499)
+                    for (int i = 0; i <= v; ++i) {
+                        const uint32_t li = __shfl_sync(0xffffffffu, C, i);
+                        Om ^= T[row(li) ^ shift_up(Sp, i, lane)];
+                    }
+                    if (lane >= d1) Om = 0;
+                    max_len = lt_len > max_len ? lt_len : max_len;
+                }
+            }
+            // park the codeword's polynomials (a unit locator for codewords that are not searched)
+            LtS[k * 36 + lane] = state == ST_OK ? (uint8_t)Lt : (lane == 0 ? 1 : 0);
+            if (lane == 0) {
+                LtS[k * 36 + 32] = state == ST_OK ? (uint8_t)Lt_top : 0;
+                meta[k * 4 + 0] = state;
+                meta[k * 4 + 1] = u;
+                meta[k * 4 + 2] = v;
+                meta[k * 4 + 3] = lt_len;
+            }
+            Ss[k * 32 + lane] = (uint8_t)Om;  // S is consumed: the slot now holds Omega'
+            __syncwarp();
+        }
+        // ---- 4. Chien search over i = 0 .. n-1 for the whole group (:1464-1475)
+        if (max_len > 0) {
+            for (int j = 0; j < max_len; ++j) {
+                const uint32_t byte = mine ? LtS[lane * 36 + j] : (j == 0 ? 1u : 0u);
+                uint32_t keep = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t pb = __ballot_sync(0xffffffffu, (byte >> b) & 1u);
+                    if (lane == b) keep = pb;
+                }
+                if (lane < 8) LP[j * 8 + lane] = keep;
+            }
+            __syncwarp();
+            for (int r = 0; r < 8 && 32 * r < rs.n; ++r) {
+                const int i = lane + 32 * r;
+                int lx = (int)(((long long)la * i) % q1);
+                lx = lx ? q1 - lx : 0;
+                build_masks(T, gf.exp[lx], mk);
+                uint32_t acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0;
+                for (int j = max_len - 1; j >= 0; --j) horner_step(mk, acc, LP + j * 8);
+                uint32_t nz = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) nz |= acc[j];
+                PM[i] = (i < rs.n && i < ns) ? ~nz : 0u;  // roots at i >= ns are not recorded (:1469-1472)
+            }
+            for (int i = 32 * ((rs.n + 31) / 32) + lane; i < 256; i += 32) PM[i] = 0;
+            __syncwarp();
+        }
+        // ---- 5. per codeword: roots, Forney, correction
+        for (int k = 0; k < ncw; ++k) {
+            const int state = meta[k * 4 + 0];
+            long long result = state == ST_FAIL ? -1 : 0;
+            if (state == ST_OK) {
+                const int u = meta[k * 4 + 1], v = meta[k * 4 + 2], lt_len = meta[k * 4 + 3];
+                uint8_t* pos = scratch + 64;
+                int v_total = 0;
+#pragma unroll 1
+                for (int r = 0; r < 8; ++r) {
+                    const int i = lane + 32 * r;
+                    const uint32_t root = (PM[i] >> k) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, root);
+                    if (root) {
+                        const int slot = v_total + __popc(bal & ((1u << lane) - 1u));
+                        if (slot < 64) pos[slot] = (uint8_t)i;
+                    }
+                    v_total += __popc(bal);
+                }
+                __syncwarp();
+                if (v_total != v + u) {  // :1479-1481
+                    result = -1;
+                } else {
+                    // Forney (:1512-1556): lane r handles root r
+                    const uint32_t Lt = LtS[k * 36 + lane], Lt_top = LtS[k * 36 + 32], Om = Ss[k * 32 + lane];
+                    const int my = lane < v_total ? pos[lane] : 0;
+                    int lx = (int)(((long long)la * my) % q1);
+                    lx = lx ? q1 - lx : 0;
+                    const uint32_t xrow = row(gf.exp[lx]);
+                    uint32_t num = 0, den = 0;
+                    for (int j = d1 - 1; j >= 0; --j) num = (uint32_t)T[xrow ^ num] ^ __shfl_sync(0xffffffffu, Om, j);
+                    for (int j = lt_len - 1; j >= 1; --j) {
+                        const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, Lt, j) : Lt_top;
+                        den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? cj : 0u);
+                    }
+                    if (lane < v_total) {
+                        uint32_t E = 0;
+                        if (den != 0) {
+                            E = gf.mul(num, gf.inv[den]);
+                            int ex = (int)(((long long)lx * (rs.c - 1)) % q1);
+                            if (ex < 0) ex += q1;
+                            E = gf.mul(E, gf.exp[ex]);
+                        }
+                        uint32_t orig = 0;  // the received symbol (0 where erased), read back from the planes
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) orig |= ((R[my * 8 + j] >> k) & 1u) << j;
+                        uint32_t fixed;
+                        if (rs.base2) {  // GF(2)'s subtract_modular rule for binary BCH (:1567-1576)
+                            const int a = (int)orig, bb = (int)E;
+                            fixed = (uint32_t)(a >= bb ? a - bb : 2 + a - bb) & 255u;
+                        } else {
+                            fixed = orig ^ E;
+                        }
+                        decoded[(cw0 + k) * ns + (ns - 1 - my)] = (uint8_t)fixed;
+                    }
+                    result = v;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) n_errors[cw0 + k] = result;
+        }
+    }
+}
+
+}  // namespace bsrs
