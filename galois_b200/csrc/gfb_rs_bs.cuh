@@ -14,11 +14,15 @@
 //      R[i][j] in shared memory; the received rows are copied to the output as they are;
 //   2. syndromes: lane l holds the 64 masks of alpha^(c+l) and runs Horner over the planes; the 8 result planes are
 //      transposed back to one byte per (codeword, syndrome);
-//   3. per codeword (warp-parallel over coefficients, products through the bank-skewed product table as in
-//      gfb_rs_fast.cuh): Gamma, S' = Gamma S, inversion-free Berlekamp-Massey, Lambda_total = Gamma Lambda, Omega' = Lambda S';
+//   3. key equation, products through the bank-skewed product table of gfb_rs_fast.cuh.  Groups without erasures: ONE
+//      THREAD PER CODEWORD — inversion-free Berlekamp-Massey and Omega' = Lambda S on byte-packed register polynomials (17
+//      coefficients: a longer locator means the word is uncorrectable or is redone by the general path), 32 codewords per warp
+//      in lock step, no cross-lane reductions.  Groups with erasures (and the overflow cases): the warp-per-codeword
+//      formulation of gfb_rs_fast.cuh (Gamma, S' = Gamma S, Berlekamp-Massey, Lambda_total = Gamma Lambda, Omega');
 //   4. Chien search: Lambda_total of the 32 codewords as planes; lane = position, 8 rounds of 32 positions, Horner with the
 //      masks of alpha^-i; a zero across the 8 result planes marks a root of codeword k in bit k;
-//   5. per codeword: root list from the bit masks, Forney, corrected symbols patched into the output row.
+//   5. one thread per codeword: root list from the bit masks, Forney for each root, corrected symbols patched into the
+//      output row.
 // Decoder failures (more than d-1 erasures, 2v + u > d - 1, wrong root count) return -1 and leave the received row.
 #pragma once
 
@@ -29,15 +33,17 @@ constexpr int kThreadsPerCta = kWarps * 32;
 constexpr int kTab = 65536;
 constexpr int kOffPlanes = 0;                  // uint32 R[256][8]
 constexpr int kOffMask = 8192;                 // uint32 [256]: erasure mask per position, later root mask per position
-constexpr int kOffS = kOffMask + 1024;         // uint8 S[32][32], later Omega'[32][32]
-constexpr int kOffLt = kOffS + 1024;           // uint8 Lambda_total[32][36] (33 used)
-constexpr int kOffLP = kOffLt + 1152;          // uint32 LP[33][8]: coefficient planes for the Chien search
-constexpr int kOffMeta = kOffLP + 1056;        // int32 meta[32][4] (state, u, v, lt_len) + 128 bytes of position scratch
-constexpr int kWarpBytes = kOffMeta + 512 + 128;
+constexpr int kRow = 36;                       // bytes per codeword row (9 words: a lane reads its row without conflicts)
+constexpr int kOffS = kOffMask + 1024;         // uint8 S[32][36], later Omega'[32][36]
+constexpr int kOffLt = kOffS + 32 * kRow;      // uint8 Lambda_total[32][36] (33 used)
+constexpr int kOffLP = kOffLt + 32 * kRow;     // uint32 LP[33][8]: coefficient planes for the Chien search; before that the
+                                               // erasure positions, after it the root positions of each codeword ([32][33])
+constexpr int kOffMeta = kOffLP + 1056;        // int32 meta[32][4] (state, u, v, lt_len)
+constexpr int kWarpBytes = kOffMeta + 512;
 constexpr size_t kSmemBytes = kTab + 512 + 256 + (size_t)kWarps * kWarpBytes;
 static_assert(kSmemBytes <= 232448, "bit-sliced decoder exceeds the shared memory of an SM");
 
-enum : int { ST_FAIL = 0, ST_CLEAN = 1, ST_OK = 2 };
+enum : int { ST_FAIL = 0, ST_CLEAN = 1, ST_OK = 2, ST_SLOW = 3 };
 
 using fastrs::row;
 using fastrs::shift_up;
@@ -69,6 +75,202 @@ __device__ __forceinline__ void horner_step(const uint32_t (&mk)[64], uint32_t (
     for (int j = 0; j < 8; ++j) acc[j] = nw[j];
 }
 
+// ---- byte-packed polynomials in registers (coefficient i = byte i of a little-endian word array) -----------------------
+template <int W>
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[W], int i) {  // i is a compile-time constant at every call site
+    return (w[i >> 2] >> (8 * (i & 3))) & 255u;
+}
+template <int W>
+__device__ __forceinline__ void shift_in_low(uint32_t (&w)[W], uint32_t in) {  // p(x) <- p(x) x + in
+#pragma unroll
+    for (int j = W - 1; j >= 1; --j) w[j] = __funnelshift_l(w[j - 1], w[j], 8);
+    w[0] = (w[0] << 8) | in;
+}
+template <int W>
+__device__ __forceinline__ void shift_out_low(uint32_t (&w)[W]) {  // drop coefficient 0
+#pragma unroll
+    for (int j = 0; j < W - 1; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], 8);
+    w[W - 1] >>= 8;
+}
+
+// Warp-per-codeword key equation for codeword k of the group (the general path: erasures, long locators).  Reads the
+// syndromes from Ss[k], writes Lambda_total to LtS[k], Omega' to Ss[k] and the codeword's state to meta[k].
+__device__ __forceinline__ void key_equation_warp(const fastrs::Tables& gf, const uint8_t* __restrict__ T, int k, int lane, int d1,
+                                                  int la, int ns, bool any_era, const uint32_t* __restrict__ PM,
+                                                  uint8_t* __restrict__ Ss, uint8_t* __restrict__ LtS, uint8_t* __restrict__ epos,
+                                                  int* __restrict__ meta) {
+    const uint32_t S = Ss[k * kRow + lane];
+    int u = 0;
+    if (any_era) {  // erasure positions of codeword k, ascending
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const int i = lane + 32 * r;
+            const uint32_t er = (i < ns) ? ((PM[i] >> k) & 1u) : 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, er);
+            if (er) {
+                const int slot = u + __popc(bal & ((1u << lane) - 1u));
+                if (slot < 64) epos[slot] = (uint8_t)i;
+            }
+            u += __popc(bal);
+        }
+        __syncwarp();
+    }
+    int state = ST_OK, v = 0, lt_len = 1;
+    uint32_t Lt = 0, Lt_top = 0, Om = 0;
+    if (u > d1) {  // :1357-1360
+        state = ST_FAIL;
+    } else if (__ballot_sync(0xffffffffu, S != 0) == 0 && u == 0) {
+        state = ST_CLEAN;  // :1373-1376
+    } else {
+        // Gamma(x) = prod (1 - Y_k x) (:1389-1393): coefficient i in lane i, coefficient 32 in Gtop
+        uint32_t Gm = lane == 0 ? 1u : 0u, Gtop = 0;
+        for (int e = 0; e < u; ++e) {
+            const uint32_t Yrow = row(gf.pow_alpha(la, (int)epos[e]));
+            const uint32_t g31 = __shfl_sync(0xffffffffu, Gm, 31);
+            Gtop ^= T[Yrow ^ g31];
+            Gm ^= T[Yrow ^ shift_up(Gm, 1, lane)];
+        }
+        // S'(x) = Gamma(x) S(x) mod x^(d-1) (:1408-1409)
+        uint32_t Sp = S;
+        if (u > 0) {
+            Sp = 0;
+            for (int i = 0; i <= u && i < 32; ++i) {
+                const uint32_t g = __shfl_sync(0xffffffffu, Gm, i);
+                Sp ^= T[row(g) ^ shift_up(S, i, lane)];
+            }
+            if (lane >= d1) Sp = 0;
+        }
+        // Berlekamp-Massey on S'[u:], inversion-free (:1421-1428, _lfsr.py:1647-1702)
+        uint32_t C = lane == 0 ? 1u : 0u, Bs = lane == 1 ? 1u : 0u, Sw = 0, b = 1;
+        int L = 0;
+        const int ls = d1 - u;
+        for (int nn = 0; nn < ls; ++nn) {
+            const uint32_t s_new = __shfl_sync(0xffffffffu, Sp, (u + nn) & 31);
+            const uint32_t up = __shfl_up_sync(0xffffffffu, Sw, 1);
+            Sw = lane == 0 ? s_new : up;
+            const uint32_t dsc = warp_xor32(T[row(C) ^ Sw]);
+            const uint32_t Cnew = (uint32_t)T[row(b) ^ C] ^ (uint32_t)T[row(dsc) ^ Bs];
+            const bool grow = dsc != 0 && 2 * L <= nn;
+            const uint32_t src = grow ? C : Bs;
+            if (dsc != 0) C = Cnew;
+            if (grow) {
+                L = nn + 1 - L;
+                b = dsc;
+            }
+            Bs = shift_up(src, 1, lane);
+        }
+        const int len = L + 1 < ls ? L + 1 : ls;
+        const uint32_t nzmask = __ballot_sync(0xffffffffu, lane < len && C != 0);
+        const int lam_len = nzmask ? 32 - __clz(nzmask) : 1;
+        if (lane >= lam_len) C = 0;
+        if (u >= d1) C = lane == 0 ? 1u : 0u;
+        v = (u < d1 ? lam_len : 1) - 1;
+        if (2 * v + u > d1) {  // :1431-1433
+            state = ST_FAIL;
+        } else {
+            Lt = C;  // Lambda_total = Gamma Lambda (:1449)
+            if (u > 0) {
+                Lt = 0;
+                for (int i = 0; i <= u; ++i) {
+                    const uint32_t g = i < 32 ? __shfl_sync(0xffffffffu, Gm, i) : Gtop;
+                    if (i < 32) Lt ^= T[row(g) ^ shift_up(C, i, lane)];
+                    if (i >= 1) Lt_top ^= T[row(g) ^ __shfl_sync(0xffffffffu, C, (32 - i) & 31)];
+                }
+            }
+            lt_len = u + v + 1;
+            for (int i = 0; i <= v; ++i) {  // Omega' = Lambda S' mod x^(d-1) (:1498-1499)
+                const uint32_t li = __shfl_sync(0xffffffffu, C, i);
+                Om ^= T[row(li) ^ shift_up(Sp, i, lane)];
+            }
+            if (lane >= d1) Om = 0;
+        }
+    }
+    __syncwarp();
+    LtS[k * kRow + lane] = state == ST_OK ? (uint8_t)Lt : (lane == 0 ? 1 : 0);  // a unit locator is never searched
+    if (lane == 0) {
+        LtS[k * kRow + 32] = state == ST_OK ? (uint8_t)Lt_top : 0;
+        meta[k * 4 + 0] = state;
+        meta[k * 4 + 1] = u;
+        meta[k * 4 + 2] = v;
+        meta[k * 4 + 3] = lt_len;
+    }
+    Ss[k * kRow + lane] = (uint8_t)Om;  // S is consumed: the slot now holds Omega'
+    __syncwarp();
+}
+
+// Thread-per-codeword key equation for a codeword WITHOUT erasures: lane k works on codeword k.  S: the d1 syndromes, one
+// per byte.  Returns the state; C receives Lambda (17 coefficients), Om the 32 coefficients of Omega' = Lambda S mod x^d1.
+__device__ __forceinline__ int key_equation_thread(const uint8_t* __restrict__ T, const uint32_t (&S)[8], int d1,
+                                                   uint32_t (&C)[5], uint32_t (&Om)[8], int& v_out) {
+    uint32_t nzS = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nzS |= S[j];
+    v_out = 0;
+    if (nzS == 0) return ST_CLEAN;  // :1373-1376
+    uint32_t Bs[5] = {0x100u, 0, 0, 0, 0};  // x^1 * B, B = 1
+    uint32_t Sw[5] = {0, 0, 0, 0, 0};       // Sw_i = S[n - i]
+    uint32_t Sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Sq[j] = S[j];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) C[j] = 0;
+    C[0] = 1;
+    uint32_t b = 1;
+    int L = 0;
+    for (int nn = 0; nn < d1; ++nn) {
+        shift_in_low(Sw, Sq[0] & 255u);
+        shift_out_low(Sq);
+        uint32_t dsc = 0;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) dsc ^= T[row(byte_of(C, i)) ^ byte_of(Sw, i)];
+        const uint32_t rb = row(b), rd = row(dsc);
+        uint32_t Cn[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            const uint32_t cn = (uint32_t)T[rb ^ byte_of(C, i)] ^ (uint32_t)T[rd ^ byte_of(Bs, i)];
+            Cn[i >> 2] |= cn << (8 * (i & 3));
+        }
+        const bool grow = dsc != 0 && 2 * L <= nn;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t src = grow ? C[j] : Bs[j];  // B <- old C (m = 1) or m += 1
+            if (dsc != 0) C[j] = Cn[j];
+            Bs[j] = src;
+        }
+        shift_in_low(Bs, 0u);
+        if (grow) {
+            L = nn + 1 - L;
+            b = dsc;
+        }
+    }
+    if (L > 16) return ST_SLOW;  // the locator may not fit 17 coefficients: the general path decides
+    // Lambda = C[:L+1] with high-degree zeros trimmed
+    const int len = L + 1 < d1 ? L + 1 : d1;
+    int lam_len = 1;
+#pragma unroll
+    for (int i = 0; i < 17; ++i)
+        if (i < len && byte_of(C, i) != 0) lam_len = i + 1;
+#pragma unroll
+    for (int i = 0; i < 17; ++i)
+        if (i >= lam_len) C[i >> 2] &= ~(255u << (8 * (i & 3)));
+    const int v = lam_len - 1;
+    v_out = v;
+    if (2 * v > d1) return ST_FAIL;  // :1431-1433
+    // Omega'_l = sum_{i <= min(l, v)} Lambda_i S_{l - i}, l < d1 (:1498-1499)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Om[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const uint32_t ri = row(byte_of(C, i));  // Lambda_i = 0 beyond the degree: T[row(0) ^ s] = 0
+#pragma unroll
+        for (int l = i; l < 32; ++l) Om[l >> 2] ^= (uint32_t)T[ri ^ byte_of(S, l - i)] << (8 * (l & 3));
+    }
+#pragma unroll
+    for (int l = 0; l < 32; ++l)
+        if (l >= d1) Om[l >> 2] &= ~(255u << (8 * (l & 3)));
+    return ST_OK;
+}
+
 __global__ void __launch_bounds__(kThreadsPerCta, 1)
     k_rs_decode_bs(RsDev rs, const uint8_t* __restrict__ tab_g, const uint8_t* __restrict__ received,
                    const uint8_t* __restrict__ erasures, int ns, uint8_t* __restrict__ decoded,
@@ -86,7 +288,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
     uint8_t* LtS = wbase + kOffLt;
     uint32_t* LP = reinterpret_cast<uint32_t*>(wbase + kOffLP);
     int* meta = reinterpret_cast<int*>(wbase + kOffMeta);
-    uint8_t* scratch = wbase + kOffMeta + 512;  // 64 bytes erasure positions, 64 bytes root positions
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_addr(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -142,23 +343,32 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             }
         }
         uint32_t any_era = 0;
-        for (int i = 0; i < ns; ++i) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
-            uint32_t b = 0, er = 0;
-            if (mine) {
-                b = rrow[ns - 1 - i];
-                er = erow ? (erow[ns - 1 - i] != 0) : 0u;
-            }
-            const uint32_t em = __ballot_sync(0xffffffffu, er);
-            if (er) b = 0;
-            any_era |= em;
-            uint32_t keep = em;  // lane 8 keeps the erasure mask, lanes 0..7 plane `lane`
+        for (int i0 = 0; i0 < ns; i0 += 8) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
+            uint32_t bb[8], ee[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t pj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
-                if (lane == j) keep = pj;
+            for (int t = 0; t < 8; ++t) {  // the eight loads are in flight together
+                const int i = i0 + t;
+                bb[t] = (mine && i < ns) ? rrow[ns - 1 - i] : 0u;
+                ee[t] = (erow && mine && i < ns) ? (erow[ns - 1 - i] != 0) : 0u;
             }
-            if (lane < 8) R[i * 8 + lane] = keep;
-            if (lane == 8) PM[i] = keep;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int i = i0 + t;
+                if (i < ns) {
+                    uint32_t b = bb[t];
+                    const uint32_t em = __ballot_sync(0xffffffffu, ee[t]);
+                    if (ee[t]) b = 0;
+                    any_era |= em;
+                    uint32_t keep = em;  // lane 8 keeps the erasure mask, lanes 0..7 plane `lane`
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t pj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
+                        if (lane == j) keep = pj;
+                    }
+                    if (lane < 8) R[i * 8 + lane] = keep;
+                    if (lane == 8) PM[i] = keep;
+                }
+            }
         }
         __syncwarp();
         // ---- 2. syndromes S_l = r(alpha^(c+l)), lane l, all 32 codewords at once (:1370)
@@ -172,119 +382,55 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                 uint32_t byte = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) byte |= ((acc[j] >> k) & 1u) << j;
-                Ss[k * 32 + lane] = lane < d1 ? (uint8_t)byte : 0;
+                Ss[k * kRow + lane] = lane < d1 ? (uint8_t)byte : 0;
             }
         }
         __syncwarp();
-        // ---- 3. per codeword: Gamma, S', Berlekamp-Massey, Lambda_total, Omega'
-        int max_len = 0;
-        for (int k = 0; k < ncw; ++k) {
-            const uint32_t S = Ss[k * 32 + lane];
-            // erasure positions of codeword k, ascending
-            int u = 0;
-            if (any_era) {
-#pragma unroll 1
-                for (int r = 0; r < 8; ++r) {
-                    const int i = lane + 32 * r;
-                    const uint32_t er = (i < ns) ? ((PM[i] >> k) & 1u) : 0u;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, er);
-                    if (er) {
-                        const int slot = u + __popc(bal & ((1u << lane) - 1u));
-                        if (slot < 64) scratch[slot] = (uint8_t)i;
-                    }
-                    u += __popc(bal);
-                }
-                __syncwarp();
+        // ---- 3. key equation
+        uint8_t* epos = reinterpret_cast<uint8_t*>(LP);  // the LP region is free until step 4
+        if (any_era == 0) {
+            uint32_t S[8], C[5], Om[8];
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(Ss + lane * kRow);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) S[j] = srow[j];
+            int v = 0;
+            int state = key_equation_thread(T, S, d1, C, Om, v);
+            if (!mine) state = ST_CLEAN;
+            const uint32_t slow = __ballot_sync(0xffffffffu, state == ST_SLOW);
+            if (state != ST_SLOW) {
+                uint32_t* lrow = reinterpret_cast<uint32_t*>(LtS + lane * kRow);
+                uint32_t* orow = reinterpret_cast<uint32_t*>(Ss + lane * kRow);
+                const bool ok = state == ST_OK;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) lrow[j] = ok ? (j < 5 ? C[j] : 0u) : (j == 0 ? 1u : 0u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) orow[j] = ok ? Om[j] : 0u;
+                meta[lane * 4 + 0] = state;
+                meta[lane * 4 + 1] = 0;
+                meta[lane * 4 + 2] = v;
+                meta[lane * 4 + 3] = v + 1;
             }
-            int state = ST_OK, v = 0, lt_len = 1;
-            uint32_t Lt = 0, Lt_top = 0, Om = 0;
-            if (u > d1) {  // :1357-1360
-                state = ST_FAIL;
-            } else if (__ballot_sync(0xffffffffu, S != 0) == 0 && u == 0) {
-                state = ST_CLEAN;  // :1373-1376
-            } else {
-                // Gamma(x) = prod (1 - Y_k x) (:1389-1393): coefficient i in lane i, coefficient 32 in Gtop
-                uint32_t Gm = lane == 0 ? 1u : 0u, Gtop = 0;
-                for (int e = 0; e < u; ++e) {
-                    const uint32_t Yrow = row(gf.pow_alpha(la, (int)scratch[e]));
-                    const uint32_t g31 = __shfl_sync(0xffffffffu, Gm, 31);
-                    Gtop ^= T[Yrow ^ g31];
-                    Gm ^= T[Yrow ^ shift_up(Gm, 1, lane)];
-                }
-                // S'(x) = Gamma(x) S(x) mod x^(d-1) (:1408-1409)
-                uint32_t Sp = S;
-                if (u > 0) {
-                    Sp = 0;
-                    for (int i = 0; i <= u && i < 32; ++i) {
-                        const uint32_t g = __shfl_sync(0xffffffffu, Gm, i);
-                        Sp ^= T[row(g) ^ shift_up(S, i, lane)];
-                    }
-                    if (lane >= d1) Sp = 0;
-                }
-                // Berlekamp-Massey on S'[u:], inversion-free (:1421-1428, _lfsr.py:1647-1702)
-                uint32_t C = lane == 0 ? 1u : 0u, Bs = lane == 1 ? 1u : 0u, Sw = 0, b = 1;
-                int L = 0;
-                const int ls = d1 - u;
-                for (int nn = 0; nn < ls; ++nn) {
-                    const uint32_t s_new = __shfl_sync(0xffffffffu, Sp, (u + nn) & 31);
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, Sw, 1);
-                    Sw = lane == 0 ? s_new : up;
-                    const uint32_t dsc = warp_xor32(T[row(C) ^ Sw]);
-                    const uint32_t Cnew = (uint32_t)T[row(b) ^ C] ^ (uint32_t)T[row(dsc) ^ Bs];
-                    const bool grow = dsc != 0 && 2 * L <= nn;
-                    const uint32_t src = grow ? C : Bs;
-                    if (dsc != 0) C = Cnew;
-                    if (grow) {
-                        L = nn + 1 - L;
-                        b = dsc;
-                    }
-                    Bs = shift_up(src, 1, lane);
-                }
-                const int len = L + 1 < ls ? L + 1 : ls;
-                const uint32_t nzmask = __ballot_sync(0xffffffffu, lane < len && C != 0);
-                const int lam_len = nzmask ? 32 - __clz(nzmask) : 1;
-                if (lane >= lam_len) C = 0;
-                if (u >= d1) C = lane == 0 ? 1u : 0u;
-                v = (u < d1 ? lam_len : 1) - 1;
-                if (2 * v + u > d1) {  // :1431-1433
-                    state = ST_FAIL;
-                } else {
-                    // Lambda_total = Gamma Lambda (:1449)
-                    Lt = C;
-                    if (u > 0) {
-                        Lt = 0;
-                        for (int i = 0; i <= u; ++i) {
-                            const uint32_t g = i < 32 ? __shfl_sync(0xffffffffu, Gm, i) : Gtop;
-                            if (i < 32) Lt ^= T[row(g) ^ shift_up(C, i, lane)];
-                            if (i >= 1) Lt_top ^= T[row(g) ^ __shfl_sync(0xffffffffu, C, (32 - i) & 31)];
-                        }
-                    }
-                    lt_len = u + v + 1;
-                    // Omega' = Lambda S' mod x^(d-1) (:1498-1499)
-                    for (int i = 0; i <= v; ++i) {
-                        const uint32_t li = __shfl_sync(0xffffffffu, C, i);
-                        Om ^= T[row(li) ^ shift_up(Sp, i, lane)];
-                    }
-                    if (lane >= d1) Om = 0;
-                    max_len = lt_len > max_len ? lt_len : max_len;
-                }
-            }
-            // park the codeword's polynomials (a unit locator for codewords that are not searched)
-            LtS[k * 36 + lane] = state == ST_OK ? (uint8_t)Lt : (lane == 0 ? 1 : 0);
-            if (lane == 0) {
-                LtS[k * 36 + 32] = state == ST_OK ? (uint8_t)Lt_top : 0;
-                meta[k * 4 + 0] = state;
-                meta[k * 4 + 1] = u;
-                meta[k * 4 + 2] = v;
-                meta[k * 4 + 3] = lt_len;
-            }
-            Ss[k * 32 + lane] = (uint8_t)Om;  // S is consumed: the slot now holds Omega'
             __syncwarp();
+            for (uint32_t m = slow; m; m &= m - 1) key_equation_warp(gf, T, __ffs(m) - 1, lane, d1, la, ns, false, PM, Ss, LtS, epos, meta);
+        } else {
+            for (int k = 0; k < ncw; ++k) key_equation_warp(gf, T, k, lane, d1, la, ns, true, PM, Ss, LtS, epos, meta);
+            if (!mine) {
+                meta[lane * 4 + 0] = ST_CLEAN;
+                meta[lane * 4 + 3] = 1;
+                LtS[lane * kRow] = 1;
+            }
+        }
+        __syncwarp();
+        int max_len = (mine && meta[lane * 4 + 0] == ST_OK) ? meta[lane * 4 + 3] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, max_len, o);
+            max_len = other > max_len ? other : max_len;
         }
         // ---- 4. Chien search over i = 0 .. n-1 for the whole group (:1464-1475)
         if (max_len > 0) {
             for (int j = 0; j < max_len; ++j) {
-                const uint32_t byte = mine ? LtS[lane * 36 + j] : (j == 0 ? 1u : 0u);
+                const uint32_t byte = mine ? LtS[lane * kRow + j] : (j == 0 ? 1u : 0u);
                 uint32_t keep = 0;
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
@@ -311,42 +457,53 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             for (int i = 32 * ((rs.n + 31) / 32) + lane; i < 256; i += 32) PM[i] = 0;
             __syncwarp();
         }
-        // ---- 5. per codeword: roots, Forney, correction
-        for (int k = 0; k < ncw; ++k) {
-            const int state = meta[k * 4 + 0];
+        // ---- 5. one thread per codeword: roots, Forney, correction
+        {
+            const int state = mine ? meta[lane * 4 + 0] : ST_CLEAN;
+            const int u = meta[lane * 4 + 1], v = meta[lane * 4 + 2];
             long long result = state == ST_FAIL ? -1 : 0;
+            uint8_t* pos = reinterpret_cast<uint8_t*>(LP) + lane * 33;  // LP is free again: root positions per codeword
+            int cnt = 0;
             if (state == ST_OK) {
-                const int u = meta[k * 4 + 1], v = meta[k * 4 + 2], lt_len = meta[k * 4 + 3];
-                uint8_t* pos = scratch + 64;
-                int v_total = 0;
-#pragma unroll 1
-                for (int r = 0; r < 8; ++r) {
-                    const int i = lane + 32 * r;
-                    const uint32_t root = (PM[i] >> k) & 1u;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, root);
-                    if (root) {
-                        const int slot = v_total + __popc(bal & ((1u << lane) - 1u));
-                        if (slot < 64) pos[slot] = (uint8_t)i;
+                for (int i = 0; i < ns; ++i) {
+                    if ((PM[i] >> lane) & 1u) {
+                        if (cnt < 33) pos[cnt] = (uint8_t)i;
+                        ++cnt;
                     }
-                    v_total += __popc(bal);
                 }
-                __syncwarp();
-                if (v_total != v + u) {  // :1479-1481
+                if (cnt != v + u) {  // :1479-1481
                     result = -1;
+                    cnt = 0;
                 } else {
-                    // Forney (:1512-1556): lane r handles root r
-                    const uint32_t Lt = LtS[k * 36 + lane], Lt_top = LtS[k * 36 + 32], Om = Ss[k * 32 + lane];
-                    const int my = lane < v_total ? pos[lane] : 0;
-                    int lx = (int)(((long long)la * my) % q1);
-                    lx = lx ? q1 - lx : 0;
-                    const uint32_t xrow = row(gf.exp[lx]);
-                    uint32_t num = 0, den = 0;
-                    for (int j = d1 - 1; j >= 0; --j) num = (uint32_t)T[xrow ^ num] ^ __shfl_sync(0xffffffffu, Om, j);
-                    for (int j = lt_len - 1; j >= 1; --j) {
-                        const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, Lt, j) : Lt_top;
-                        den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? cj : 0u);
-                    }
-                    if (lane < v_total) {
+                    result = v;
+                }
+            }
+            int max_cnt = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int other = __shfl_xor_sync(0xffffffffu, max_cnt, o);
+                max_cnt = other > max_cnt ? other : max_cnt;
+            }
+            if (max_cnt > 0) {
+                uint32_t Lt[9], Om[8];
+                const uint32_t* lrow = reinterpret_cast<const uint32_t*>(LtS + lane * kRow);
+                const uint32_t* orow = reinterpret_cast<const uint32_t*>(Ss + lane * kRow);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) Lt[j] = lrow[j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Om[j] = orow[j];
+                for (int r = 0; r < max_cnt; ++r) {
+                    if (r < cnt) {
+                        // Forney (:1512-1556): E = Omega'(X^-1) / Lambda_total'(X^-1) * (X^-1)^(c-1); characteristic 2
+                        const int my = pos[r];
+                        int lx = (int)(((long long)la * my) % q1);
+                        lx = lx ? q1 - lx : 0;
+                        const uint32_t xrow = row(gf.exp[lx]);
+                        uint32_t num = 0, den = 0;
+#pragma unroll
+                        for (int j = 31; j >= 0; --j) num = (uint32_t)T[xrow ^ num] ^ byte_of(Om, j);  // Omega'_j = 0 for j >= d1
+#pragma unroll
+                        for (int j = 32; j >= 1; --j) den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? byte_of(Lt, j) : 0u);
                         uint32_t E = 0;
                         if (den != 0) {
                             E = gf.mul(num, gf.inv[den]);
@@ -356,7 +513,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                         }
                         uint32_t orig = 0;  // the received symbol (0 where erased), read back from the planes
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) orig |= ((R[my * 8 + j] >> k) & 1u) << j;
+                        for (int j = 0; j < 8; ++j) orig |= ((R[my * 8 + j] >> lane) & 1u) << j;
                         uint32_t fixed;
                         if (rs.base2) {  // GF(2)'s subtract_modular rule for binary BCH (:1567-1576)
                             const int a = (int)orig, bb = (int)E;
@@ -364,14 +521,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                         } else {
                             fixed = orig ^ E;
                         }
-                        decoded[(cw0 + k) * ns + (ns - 1 - my)] = (uint8_t)fixed;
+                        decoded[(cw0 + lane) * ns + (ns - 1 - my)] = (uint8_t)fixed;
                     }
-                    result = v;
                 }
-                __syncwarp();
             }
-            if (lane == 0) n_errors[cw0 + k] = result;
+            if (mine) n_errors[cw0 + lane] = result;
         }
+        __syncwarp();
     }
 }
 
