@@ -59,6 +59,24 @@ __device__ __forceinline__ void build_masks(const uint8_t* __restrict__ T, uint3
 #pragma unroll
         for (int j = 0; j < 8; ++j) mk[j * 8 + b] = 0u - ((cb >> j) & 1u);
     }
+    // keep the masks as opaque register values: left to itself the compiler re-derives them as predicates inside the Horner
+    // loop (one SEL plus one LOP3 per term instead of one LOP3)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(mk[i]));
+}
+
+// 32 x 32 bit transpose across the warp: on return bit k of lane m is bit m of lane k's input
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m0 = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        const bool hi = (lane & s) != 0;
+        const uint32_t keep = hi ? ~m0 : m0;
+        const uint32_t t = hi ? (y >> s) : (y << s);
+        x = (x & keep) | (t & ~keep);
+    }
+    return x;
 }
 
 // acc <- x * acc + add on 8 bit-planes (32 independent field elements)
@@ -198,54 +216,51 @@ __device__ __forceinline__ void key_equation_warp(const fastrs::Tables& gf, cons
     __syncwarp();
 }
 
-// Thread-per-codeword key equation for a codeword WITHOUT erasures: lane k works on codeword k.  S: the d1 syndromes, one
-// per byte.  Returns the state; C receives Lambda (17 coefficients), Om the 32 coefficients of Omega' = Lambda S mod x^d1.
-__device__ __forceinline__ int key_equation_thread(const uint8_t* __restrict__ T, const uint32_t (&S)[8], int d1,
-                                                   uint32_t (&C)[5], uint32_t (&Om)[8], int& v_out) {
-    uint32_t nzS = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) nzS |= S[j];
-    v_out = 0;
-    if (nzS == 0) return ST_CLEAN;  // :1373-1376
+// Inversion-free Berlekamp-Massey (_lfsr.py:1647-1702) on the sequence in Sq (one element per byte, `ls` of them), one
+// thread per sequence; `ls_max` is the loop bound shared by the warp.  C receives the connection polynomial (17
+// coefficients); returns L (a value above 16 means C overflowed and is not usable).
+__device__ __forceinline__ int bm_thread(const uint8_t* __restrict__ T, uint32_t (&Sq)[8], int ls, int ls_max, uint32_t (&C)[5]) {
     uint32_t Bs[5] = {0x100u, 0, 0, 0, 0};  // x^1 * B, B = 1
     uint32_t Sw[5] = {0, 0, 0, 0, 0};       // Sw_i = S[n - i]
-    uint32_t Sq[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Sq[j] = S[j];
 #pragma unroll
     for (int j = 0; j < 5; ++j) C[j] = 0;
     C[0] = 1;
     uint32_t b = 1;
     int L = 0;
-    for (int nn = 0; nn < d1; ++nn) {
-        shift_in_low(Sw, Sq[0] & 255u);
-        shift_out_low(Sq);
-        uint32_t dsc = 0;
+    for (int nn = 0; nn < ls_max; ++nn) {
+        if (nn < ls) {
+            shift_in_low(Sw, Sq[0] & 255u);
+            shift_out_low(Sq);
+            uint32_t dsc = 0;
 #pragma unroll
-        for (int i = 0; i < 17; ++i) dsc ^= T[row(byte_of(C, i)) ^ byte_of(Sw, i)];
-        const uint32_t rb = row(b), rd = row(dsc);
-        uint32_t Cn[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < 17; ++i) dsc ^= T[row(byte_of(C, i)) ^ byte_of(Sw, i)];
+            const uint32_t rb = row(b), rd = row(dsc);
+            uint32_t Cn[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 17; ++i) {
-            const uint32_t cn = (uint32_t)T[rb ^ byte_of(C, i)] ^ (uint32_t)T[rd ^ byte_of(Bs, i)];
-            Cn[i >> 2] |= cn << (8 * (i & 3));
-        }
-        const bool grow = dsc != 0 && 2 * L <= nn;
+            for (int i = 0; i < 17; ++i) {
+                const uint32_t cn = (uint32_t)T[rb ^ byte_of(C, i)] ^ (uint32_t)T[rd ^ byte_of(Bs, i)];
+                Cn[i >> 2] |= cn << (8 * (i & 3));
+            }
+            const bool grow = dsc != 0 && 2 * L <= nn;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const uint32_t src = grow ? C[j] : Bs[j];  // B <- old C (m = 1) or m += 1
-            if (dsc != 0) C[j] = Cn[j];
-            Bs[j] = src;
-        }
-        shift_in_low(Bs, 0u);
-        if (grow) {
-            L = nn + 1 - L;
-            b = dsc;
+            for (int j = 0; j < 5; ++j) {
+                const uint32_t src = grow ? C[j] : Bs[j];  // B <- old C (m = 1) or m += 1
+                if (dsc != 0) C[j] = Cn[j];
+                Bs[j] = src;
+            }
+            shift_in_low(Bs, 0u);
+            if (grow) {
+                L = nn + 1 - L;
+                b = dsc;
+            }
         }
     }
-    if (L > 16) return ST_SLOW;  // the locator may not fit 17 coefficients: the general path decides
-    // Lambda = C[:L+1] with high-degree zeros trimmed
-    const int len = L + 1 < d1 ? L + 1 : d1;
+    return L;
+}
+
+// Lambda = C[:min(L + 1, ls)] with high-degree zeros trimmed; returns its length
+__device__ __forceinline__ int trim_locator(uint32_t (&C)[5], int L, int ls) {
+    const int len = L + 1 < ls ? L + 1 : ls;
     int lam_len = 1;
 #pragma unroll
     for (int i = 0; i < 17; ++i)
@@ -253,21 +268,135 @@ __device__ __forceinline__ int key_equation_thread(const uint8_t* __restrict__ T
 #pragma unroll
     for (int i = 0; i < 17; ++i)
         if (i >= lam_len) C[i >> 2] &= ~(255u << (8 * (i & 3)));
-    const int v = lam_len - 1;
-    v_out = v;
-    if (2 * v > d1) return ST_FAIL;  // :1431-1433
-    // Omega'_l = sum_{i <= min(l, v)} Lambda_i S_{l - i}, l < d1 (:1498-1499)
+    return lam_len;
+}
+
+// Omega'_l = sum_{i <= l} Lambda_i S_{l - i}, l < d1 (:1498-1499); Lambda_i = 0 beyond the degree and T[row(0) ^ s] = 0
+__device__ __forceinline__ void omega_thread(const uint8_t* __restrict__ T, const uint32_t (&C)[5], const uint32_t (&S)[8], int d1,
+                                             uint32_t (&Om)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) Om[j] = 0;
 #pragma unroll
     for (int i = 0; i < 17; ++i) {
-        const uint32_t ri = row(byte_of(C, i));  // Lambda_i = 0 beyond the degree: T[row(0) ^ s] = 0
+        const uint32_t ri = row(byte_of(C, i));
 #pragma unroll
         for (int l = i; l < 32; ++l) Om[l >> 2] ^= (uint32_t)T[ri ^ byte_of(S, l - i)] << (8 * (l & 3));
     }
 #pragma unroll
     for (int l = 0; l < 32; ++l)
         if (l >= d1) Om[l >> 2] &= ~(255u << (8 * (l & 3)));
+}
+
+// Thread-per-codeword key equation for a group WITHOUT erasures: lane k works on codeword k.  S: the d1 syndromes, one per
+// byte.  Returns the state; Lt receives Lambda (17 coefficients), Om the coefficients of Omega' = Lambda S mod x^d1.
+__device__ __forceinline__ int key_equation_thread(const uint8_t* __restrict__ T, const uint32_t (&S)[8], int d1,
+                                                   uint32_t (&Lt)[9], uint32_t (&Om)[8], int& v_out) {
+    uint32_t nzS = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nzS |= S[j];
+    v_out = 0;
+    if (nzS == 0) return ST_CLEAN;  // :1373-1376
+    uint32_t Sq[8], C[5];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Sq[j] = S[j];
+    const int L = bm_thread(T, Sq, d1, d1, C);
+    if (L > 16) return ST_SLOW;  // the locator may not fit 17 coefficients: the general path decides
+    const int v = trim_locator(C, L, d1) - 1;
+    v_out = v;
+    if (2 * v > d1) return ST_FAIL;  // :1431-1433
+    omega_thread(T, C, S, d1, Om);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) Lt[j] = j < 5 ? C[j] : 0u;
+    return ST_OK;
+}
+
+// The same with erasures: lane k holds the u erasure positions of codeword k in epos (ascending, at most 33 stored); u_max is
+// the largest u of the group.  Lt receives Lambda_total = Gamma Lambda (33 coefficients), Om the coefficients of Omega'.
+__device__ __forceinline__ int key_equation_thread_era(const fastrs::Tables& gf, const uint8_t* __restrict__ T, const uint32_t (&S)[8],
+                                                       int d1, int la, int u, int u_max, const uint8_t* __restrict__ epos,
+                                                       uint32_t (&Lt)[9], uint32_t (&Om)[8], int& v_out) {
+    v_out = 0;
+    if (u > d1) return ST_FAIL;  // :1357-1360
+    uint32_t nzS = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nzS |= S[j];
+    if (nzS == 0 && u == 0) return ST_CLEAN;  // :1373-1376
+    // Gamma(x) = prod (1 - Y_e x) (:1389-1393), 33 coefficients
+    uint32_t G[9] = {1u, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int ub = u_max < 32 ? u_max : 32;
+    for (int e = 0; e < ub; ++e) {
+        if (e < u) {
+            const uint32_t Yrow = row(gf.exp[((uint32_t)la * (uint32_t)epos[e]) % (uint32_t)gf.q1]);
+            uint32_t Gn[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) Gn[j] = G[j];
+#pragma unroll
+            for (int i = 1; i <= 32; ++i) Gn[i >> 2] ^= (uint32_t)T[Yrow ^ byte_of(G, i - 1)] << (8 * (i & 3));
+#pragma unroll
+            for (int j = 0; j < 9; ++j) G[j] = Gn[j];
+        }
+    }
+    // S'(x) = Gamma(x) S(x) mod x^(d-1) (:1408-1409)
+    uint32_t Sp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i <= u_max) {  // uniform: Gamma_i = 0 beyond the largest erasure count
+            const uint32_t ri = row(byte_of(G, i));
+#pragma unroll
+            for (int l = i; l < 32; ++l) Sp[l >> 2] ^= (uint32_t)T[ri ^ byte_of(S, l - i)] << (8 * (l & 3));
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 32; ++l)
+        if (l >= d1) Sp[l >> 2] &= ~(255u << (8 * (l & 3)));
+    // Berlekamp-Massey on S'[u:] (:1421-1428)
+    uint32_t Sq[8], C[5];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Sq[j] = Sp[j];
+    {  // drop the u low coefficients: whole words, then bytes
+        const int wq = u >> 2, bq = 8 * (u & 3);
+        if (wq & 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Sq[j] = j + 4 < 8 ? Sq[j + 4] : 0u;
+        }
+        if (wq & 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Sq[j] = j + 2 < 8 ? Sq[j + 2] : 0u;
+        }
+        if (wq & 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Sq[j] = j + 1 < 8 ? Sq[j + 1] : 0u;
+        }
+        if (wq & 8) {  // u = 32
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Sq[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) Sq[j] = __funnelshift_r(Sq[j], Sq[j + 1], bq);
+        Sq[7] >>= bq;
+    }
+    const int ls = d1 - u;
+    const int L = bm_thread(T, Sq, ls, d1, C);
+    if (L > 16) return ST_SLOW;
+    int v = 0;
+    if (u >= d1) {  // no syndromes left for the errors: Lambda = 1
+#pragma unroll
+        for (int j = 0; j < 5; ++j) C[j] = j == 0 ? 1u : 0u;
+    } else {
+        v = trim_locator(C, L, ls) - 1;
+    }
+    v_out = v;
+    if (2 * v + u > d1) return ST_FAIL;  // :1431-1433
+    // Lambda_total = Gamma Lambda (:1449), degree u + v <= 32
+#pragma unroll
+    for (int j = 0; j < 9; ++j) Lt[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        const uint32_t ri = row(byte_of(C, i));
+#pragma unroll
+        for (int l = i; l <= 32; ++l) Lt[l >> 2] ^= (uint32_t)T[ri ^ byte_of(G, l - i)] << (8 * (l & 3));
+    }
+    omega_thread(T, C, Sp, d1, Om);
     return ST_OK;
 }
 
@@ -317,6 +446,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
     const int d1 = rs.d - 1;  // <= 32
     const int la = rs.log_alpha;
     const int q1 = rs.q1;
+    const int cm1 = (int)((((long long)rs.c - 1) % q1 + q1) % q1);  // c - 1 as an exponent of the multiplicative group
     const size_t groups = (N + 31) / 32;
     const size_t warps_total = (size_t)gridDim.x * kWarps;
     uint32_t mk[64];
@@ -333,7 +463,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             const uint8_t* src = received + cw0 * ns;
             uint8_t* dst = decoded + cw0 * ns;
             const size_t bytes = (size_t)ncw * ns;
-            if ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+            if ((((uintptr_t)src | (uintptr_t)dst | bytes) & 15) == 0) {  // full groups: 8160 bytes
+                const uint4* s16 = reinterpret_cast<const uint4*>(src);
+                uint4* d16 = reinterpret_cast<uint4*>(dst);
+                const int n16 = (int)(bytes / 16);
+                for (int i0 = lane; i0 < n16; i0 += 8 * 32) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (i0 + 32 * t < n16) v[t] = __ldg(s16 + i0 + 32 * t);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (i0 + 32 * t < n16) d16[i0 + 32 * t] = v[t];
+                }
+            } else if ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
                 const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
                 uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
                 for (size_t i = lane; i < bytes / 4; i += 32) d4[i] = s4[i];
@@ -343,32 +486,38 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             }
         }
         uint32_t any_era = 0;
-        for (int i0 = 0; i0 < ns; i0 += 8) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
-            uint32_t bb[8], ee[8];
+        for (int i0 = 0; i0 < 256; i0 += 16) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (mine) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {  // the eight loads are in flight together
-                const int i = i0 + t;
-                bb[t] = (mine && i < ns) ? rrow[ns - 1 - i] : 0u;
-                ee[t] = (erow && mine && i < ns) ? (erow[ns - 1 - i] != 0) : 0u;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int i = i0 + t;
-                if (i < ns) {
-                    uint32_t b = bb[t];
-                    const uint32_t em = __ballot_sync(0xffffffffu, ee[t]);
-                    if (ee[t]) b = 0;
-                    any_era |= em;
-                    uint32_t keep = em;  // lane 8 keeps the erasure mask, lanes 0..7 plane `lane`
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t pj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
-                        if (lane == j) keep = pj;
-                    }
-                    if (lane < 8) R[i * 8 + lane] = keep;
-                    if (lane == 8) PM[i] = keep;
+                for (int t = 0; t < 16; ++t) {  // sixteen loads in flight
+                    const int i = i0 + t;
+                    const uint32_t b = i < ns ? rrow[ns - 1 - i] : 0u;
+                    w[t >> 2] |= b << (8 * (t & 3));
                 }
             }
+            if (erow) {  // uniform
+                uint32_t ew[4] = {0, 0, 0, 0};
+                if (mine) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int i = i0 + t;
+                        const uint32_t e = (i < ns && erow[ns - 1 - i] != 0) ? 255u : 0u;
+                        ew[t >> 2] |= e << (8 * (t & 3));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    w[q] &= ~ew[q];
+                    const uint32_t em = transpose32(ew[q], lane);  // lane 8t: erasure mask of position i0 + 4q + t
+                    any_era |= __ballot_sync(0xffffffffu, em != 0);
+                    if ((lane & 7) == 0) PM[i0 + 4 * q + (lane >> 3)] = em;
+                }
+            } else {
+                if (lane < 16) PM[i0 + lane] = 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) R[(i0 + 4 * q) * 8 + lane] = transpose32(w[q], lane);  // lane 8t + j: plane j of position + t
         }
         __syncwarp();
         // ---- 2. syndromes S_l = r(alpha^(c+l)), lane l, all 32 codewords at once (:1370)
@@ -386,15 +535,33 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             }
         }
         __syncwarp();
-        // ---- 3. key equation
+        // ---- 3. key equation, one thread per codeword
         uint8_t* epos = reinterpret_cast<uint8_t*>(LP);  // the LP region is free until step 4
-        if (any_era == 0) {
-            uint32_t S[8], C[5], Om[8];
+        {
+            uint32_t S[8], Lt[9], Om[8];
             const uint32_t* srow = reinterpret_cast<const uint32_t*>(Ss + lane * kRow);
 #pragma unroll
             for (int j = 0; j < 8; ++j) S[j] = srow[j];
-            int v = 0;
-            int state = key_equation_thread(T, S, d1, C, Om, v);
+            int v = 0, u = 0, state;
+            if (any_era == 0) {
+                state = key_equation_thread(T, S, d1, Lt, Om, v);
+            } else {
+                uint8_t* ep = epos + lane * 33;  // erasure positions of codeword `lane`, ascending
+#pragma unroll 1
+                for (int r = 0; r < 8; ++r) {
+                    for (uint32_t m = transpose32(PM[32 * r + lane], lane); m; m &= m - 1) {
+                        if (u < 33) ep[u] = (uint8_t)(32 * r + __ffs(m) - 1);
+                        ++u;
+                    }
+                }
+                int u_max = u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int other = __shfl_xor_sync(0xffffffffu, u_max, o);
+                    u_max = other > u_max ? other : u_max;
+                }
+                state = key_equation_thread_era(gf, T, S, d1, la, u, u_max, ep, Lt, Om, v);
+            }
             if (!mine) state = ST_CLEAN;
             const uint32_t slow = __ballot_sync(0xffffffffu, state == ST_SLOW);
             if (state != ST_SLOW) {
@@ -402,23 +569,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                 uint32_t* orow = reinterpret_cast<uint32_t*>(Ss + lane * kRow);
                 const bool ok = state == ST_OK;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) lrow[j] = ok ? (j < 5 ? C[j] : 0u) : (j == 0 ? 1u : 0u);
+                for (int j = 0; j < 9; ++j) lrow[j] = ok ? Lt[j] : (j == 0 ? 1u : 0u);  // a unit locator is never searched
 #pragma unroll
                 for (int j = 0; j < 8; ++j) orow[j] = ok ? Om[j] : 0u;
                 meta[lane * 4 + 0] = state;
-                meta[lane * 4 + 1] = 0;
+                meta[lane * 4 + 1] = u;
                 meta[lane * 4 + 2] = v;
-                meta[lane * 4 + 3] = v + 1;
+                meta[lane * 4 + 3] = u + v + 1;
             }
             __syncwarp();
-            for (uint32_t m = slow; m; m &= m - 1) key_equation_warp(gf, T, __ffs(m) - 1, lane, d1, la, ns, false, PM, Ss, LtS, epos, meta);
-        } else {
-            for (int k = 0; k < ncw; ++k) key_equation_warp(gf, T, k, lane, d1, la, ns, true, PM, Ss, LtS, epos, meta);
-            if (!mine) {
-                meta[lane * 4 + 0] = ST_CLEAN;
-                meta[lane * 4 + 3] = 1;
-                LtS[lane * kRow] = 1;
-            }
+            for (uint32_t m = slow; m; m &= m - 1)  // long locators: the warp-per-codeword formulation
+                key_equation_warp(gf, T, __ffs(m) - 1, lane, d1, la, ns, any_era != 0, PM, Ss, LtS, epos, meta);
         }
         __syncwarp();
         int max_len = (mine && meta[lane * 4 + 0] == ST_OK) ? meta[lane * 4 + 3] : 0;
@@ -442,7 +603,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             __syncwarp();
             for (int r = 0; r < 8 && 32 * r < rs.n; ++r) {
                 const int i = lane + 32 * r;
-                int lx = (int)(((long long)la * i) % q1);
+                int lx = (int)(((uint32_t)la * (uint32_t)i) % (uint32_t)q1);  // la < q1 <= 255, i < 256
                 lx = lx ? q1 - lx : 0;
                 build_masks(T, gf.exp[lx], mk);
                 uint32_t acc[8];
@@ -464,10 +625,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
             long long result = state == ST_FAIL ? -1 : 0;
             uint8_t* pos = reinterpret_cast<uint8_t*>(LP) + lane * 33;  // LP is free again: root positions per codeword
             int cnt = 0;
+            uint32_t rootw[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) rootw[r] = max_len > 0 ? transpose32(PM[32 * r + lane], lane) : 0u;  // bit m: position 32 r + m
             if (state == ST_OK) {
-                for (int i = 0; i < ns; ++i) {
-                    if ((PM[i] >> lane) & 1u) {
-                        if (cnt < 33) pos[cnt] = (uint8_t)i;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    for (uint32_t m = rootw[r]; m; m &= m - 1) {
+                        if (cnt < 33) pos[cnt] = (uint8_t)(32 * r + __ffs(m) - 1);
                         ++cnt;
                     }
                 }
@@ -492,23 +657,39 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                 for (int j = 0; j < 9; ++j) Lt[j] = lrow[j];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) Om[j] = orow[j];
+                // highest coefficient any lane of the group needs: the Horner chains below stop there
+                int dO = 0, dL = 1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (Om[j]) dO = 4 * j + 3 - (__clz(Om[j]) >> 3);
+#pragma unroll
+                for (int j = 0; j < 9; ++j)
+                    if (Lt[j]) dL = 4 * j + 3 - (__clz(Lt[j]) >> 3);
+                if (cnt == 0) dO = 0, dL = 1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int a = __shfl_xor_sync(0xffffffffu, dO, o), c = __shfl_xor_sync(0xffffffffu, dL, o);
+                    dO = a > dO ? a : dO;
+                    dL = c > dL ? c : dL;
+                }
                 for (int r = 0; r < max_cnt; ++r) {
                     if (r < cnt) {
                         // Forney (:1512-1556): E = Omega'(X^-1) / Lambda_total'(X^-1) * (X^-1)^(c-1); characteristic 2
                         const int my = pos[r];
-                        int lx = (int)(((long long)la * my) % q1);
+                        int lx = (int)(((uint32_t)la * (uint32_t)my) % (uint32_t)q1);
                         lx = lx ? q1 - lx : 0;
                         const uint32_t xrow = row(gf.exp[lx]);
                         uint32_t num = 0, den = 0;
 #pragma unroll
-                        for (int j = 31; j >= 0; --j) num = (uint32_t)T[xrow ^ num] ^ byte_of(Om, j);  // Omega'_j = 0 for j >= d1
+                        for (int j = 31; j >= 0; --j)
+                            if (j <= dO) num = (uint32_t)T[xrow ^ num] ^ byte_of(Om, j);
 #pragma unroll
-                        for (int j = 32; j >= 1; --j) den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? byte_of(Lt, j) : 0u);
+                        for (int j = 32; j >= 1; --j)
+                            if (j <= dL) den = (uint32_t)T[xrow ^ den] ^ ((j & 1) ? byte_of(Lt, j) : 0u);
                         uint32_t E = 0;
                         if (den != 0) {
                             E = gf.mul(num, gf.inv[den]);
-                            int ex = (int)(((long long)lx * (rs.c - 1)) % q1);
-                            if (ex < 0) ex += q1;
+                            const int ex = (int)(((uint32_t)lx * (uint32_t)cm1) % (uint32_t)q1);
                             E = gf.mul(E, gf.exp[ex]);
                         }
                         uint32_t orig = 0;  // the received symbol (0 where erased), read back from the planes

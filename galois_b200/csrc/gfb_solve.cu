@@ -26,6 +26,7 @@
 //   k_lu_pivot    (1 CTA)   find the pivot, exchange; publish the pivot row (rowbuf) and the column multipliers (colbuf)
 //   k_eliminate   (grid)    A[r][c] -= colbuf[r] * rowbuf[c] for the rows below, columns c >= i, 256 columns x 32 rows per CTA
 #include <climits>
+#include <type_traits>
 
 #include "gfb_common.cuh"
 #include "gfb_dispatch.cuh"
@@ -94,18 +95,24 @@ struct PanelMeta {
 // global memory and each row segment is updated through fully unrolled, independent loads.
 constexpr int kSlabStride = kPanel + 1;
 
+// storage type of the panel slab: in shared memory a field whose elements fit 32 bits is held as uint32 even when the
+// array dtype is wider (a 1024-row slab of an int64 array then fits beside the field tables)
+template <typename T, typename E, bool SMEM>
+using SlabT = std::conditional_t<(SMEM && sizeof(E) < sizeof(T)), E, T>;
+
 template <typename T, typename F, bool SMEM>
 __global__ void __launch_bounds__(kPivotThreads)
 k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, ElimState* st, PanelMeta* meta,
            typename F::elem* __restrict__ M, size_t fs) {
     using E = typename F::elem;
+    using S = SlabT<T, E, SMEM>;  // the shared-memory slab holds field elements in their compute width
     extern __shared__ uint4 smem_raw[];
     f.init_smem(smem_raw);
-    T* s_slab = reinterpret_cast<T*>(reinterpret_cast<char*>(smem_raw) + fs);
+    S* s_slab = reinterpret_cast<S*>(reinterpret_cast<char*>(smem_raw) + fs);
     __shared__ int s_min;
     __shared__ E s_prow[kPanel];
     __shared__ E s_pinv;
-    auto at = [&](size_t r, int t) -> T& {
+    auto at = [&](size_t r, int t) -> S& {
         if constexpr (SMEM)
             return s_slab[r * kSlabStride + t];
         else
@@ -115,7 +122,7 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
         for (size_t idx = threadIdx.x; idx < rows * (size_t)kw; idx += blockDim.x) {
             const size_t r = idx / kw;
             const int t = (int)(idx - r * kw);
-            s_slab[r * kSlabStride + t] = A[r * cols + j0 + t];
+            s_slab[r * kSlabStride + t] = (S)A[r * cols + j0 + t];
         }
     }
     int p = st->p;
@@ -131,7 +138,7 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
             __syncthreads();
             int cand = INT_MAX;
             for (size_t r = (size_t)p + threadIdx.x; r < rows; r += blockDim.x) {
-                if (at(r, s) != (T)0) {
+                if (at(r, s) != (S)0) {
                     cand = (int)r;
                     break;  // later rows of this thread are larger
                 }
@@ -147,7 +154,7 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
             __syncthreads();  // s_min is rewritten by the next step
             continue;
         }
-        const E piv = to_elem<E, T>(at(i, s));
+        const E piv = to_elem<E, S>(at(i, s));
         __syncthreads();  // the pivot has been read by everyone before row i moves
         // thread 0 inverts the pivot (a ~45-multiply dependent chain) while warps 1 and 2 exchange rows p and i of the
         // slab and of the multipliers recorded by the earlier steps
@@ -157,7 +164,7 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
             const int t = (threadIdx.x & 31);
             if (threadIdx.x < 64) {
                 if (t < kw) {
-                    const T a = at(p, t);
+                    const S a = at(p, t);
                     at(p, t) = at(i, t);
                     at(i, t) = a;
                 }
@@ -170,19 +177,19 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
         __syncthreads();
         const E pinv = s_pinv;
         if ((int)threadIdx.x < kw) {  // row p /= pivot (its entries left of column j0 + s are already zero)
-            const E v = f.mul(to_elem<E, T>(at(p, threadIdx.x)), pinv);
+            const E v = f.mul(to_elem<E, S>(at(p, threadIdx.x)), pinv);
             s_prow[threadIdx.x] = f.premul(v);  // multiplier form: one reduction per product below
-            at(p, threadIdx.x) = to_store<T, E>(v);
+            at(p, threadIdx.x) = to_store<S, E>(v);
         }
         __syncthreads();
         for (size_t r = threadIdx.x; r < rows; r += blockDim.x) {
             E m = f.zero();
             if (r != (size_t)p) {
-                m = to_elem<E, T>(at(r, s));
+                m = to_elem<E, S>(at(r, s));
                 if (!f.is_zero(m)) {
 #pragma unroll 4
                     for (int t = s; t < kw; ++t)
-                        at(r, t) = to_store<T, E>(f.sub(to_elem<E, T>(at(r, t)), f.mul_prepared(m, s_prow[t])));
+                        at(r, t) = to_store<S, E>(f.sub(to_elem<E, S>(at(r, t)), f.mul_prepared(m, s_prow[t])));
                 }
             }
             M[r * kPanel + s] = m;
@@ -201,7 +208,7 @@ k_rr_panel(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, 
         for (size_t idx = threadIdx.x; idx < rows * (size_t)kw; idx += blockDim.x) {
             const size_t r = idx / kw;
             const int t = (int)(idx - r * kw);
-            A[r * cols + j0 + t] = s_slab[r * kSlabStride + t];
+            A[r * cols + j0 + t] = (T)s_slab[r * kSlabStride + t];
         }
     }
     if (threadIdx.x == 0) {
@@ -547,7 +554,7 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
         if (rows && cols) {
             if ((rows + kUpdRows - 1) / kUpdRows > 65535) return GFB_ERR_UNSUPPORTED;
             // the panel slab lives in shared memory when rows * 33 entries fit beside the field tables
-            const size_t slab_bytes = align16(rows * kSlabStride * sizeof(T));
+            const size_t slab_bytes = align16(rows * kSlabStride * sizeof(SlabT<T, E, true>));
             const bool slab_in_smem = fs + slab_bytes <= (size_t)200 * 1024;
             if (slab_in_smem)
                 GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
