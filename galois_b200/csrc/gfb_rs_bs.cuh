@@ -10,18 +10,19 @@
 // m x m bit matrix, so with the symbols of 32 codewords held as m bit-planes (bit k of plane j = bit j of codeword k's
 // symbol) one Horner step for 32 codewords is 64 LOP3 (`acc_b & mask_jb ^ ...`) and 8 broadcast loads — no tables, no
 // conflicts, 0.08 instructions per multiply-add.
-//   1. load: lane k reads codeword k's symbols (erasures zeroed); 8 warp ballots per position turn them into planes
-//      R[i][j] in shared memory; the received rows are copied to the output as they are;
+//   1. load: lane k reads codeword k's symbols (erasures zeroed) four to a word; a 32 x 32 bit transpose across the warp
+//      (five shuffle stages) turns each word into the planes R[i][j] of four positions; the received rows are copied to the
+//      output as they are (16-byte accesses);
 //   2. syndromes: lane l holds the 64 masks of alpha^(c+l) and runs Horner over the planes; the 8 result planes are
 //      transposed back to one byte per (codeword, syndrome);
-//   3. key equation, products through the bank-skewed product table of gfb_rs_fast.cuh.  Groups without erasures: ONE
-//      THREAD PER CODEWORD — inversion-free Berlekamp-Massey and Omega' = Lambda S on byte-packed register polynomials (17
-//      coefficients: a longer locator means the word is uncorrectable or is redone by the general path), 32 codewords per warp
-//      in lock step, no cross-lane reductions.  Groups with erasures (and the overflow cases): the warp-per-codeword
-//      formulation of gfb_rs_fast.cuh (Gamma, S' = Gamma S, Berlekamp-Massey, Lambda_total = Gamma Lambda, Omega');
+//   3. key equation, ONE THREAD PER CODEWORD, products through the bank-skewed product table of gfb_rs_fast.cuh, polynomials
+//      byte-packed in registers: Gamma and S' = Gamma S when the group has erasures, inversion-free Berlekamp-Massey (17
+//      coefficients: a longer connection polynomial is redone by the warp-per-codeword formulation of gfb_rs_fast.cuh),
+//      Lambda_total = Gamma Lambda, Omega' = Lambda S' — 32 codewords per warp in lock step, no cross-lane reductions;
 //   4. Chien search: Lambda_total of the 32 codewords as planes; lane = position, 8 rounds of 32 positions, Horner with the
 //      masks of alpha^-i; a zero across the 8 result planes marks a root of codeword k in bit k;
-//   5. one thread per codeword: root list from the bit masks, Forney for each root, corrected symbols patched into the
+//   5. one thread per codeword: root list from the (transposed) bit masks, Forney for each root with the Horner chains cut at
+//      the group's highest degree, corrected symbols patched into the
 //      output row.
 // Decoder failures (more than d-1 erasures, 2v + u > d - 1, wrong root count) return -1 and leave the received row.
 #pragma once
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
     const size_t warps_total = (size_t)gridDim.x * kWarps;
     uint32_t mk[64];
 
-    for (size_t grp = (size_t)blockIdx.x * kWarps + warp; grp < groups; grp += warps_total) {
+    for (size_t grp = (size_t)blockIdx.x + (size_t)gridDim.x * warp; grp < groups; grp += warps_total) {
         const size_t cw0 = grp * 32;
         const int ncw = (int)(N - cw0 < 32 ? N - cw0 : 32);
         const bool mine = lane < ncw;
