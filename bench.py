@@ -418,7 +418,8 @@ class RsDecode:
     n_err, n_era = 16, 0
 
     metric, unit, dtype, scaling = "rs255_223_decode_cw_per_sec", "codeword/s", "u8", "strong"
-    kernel = "k_rs_decode"
+    kernel = "k_rs_decode_bs"
+    d1 = 32  # parity symbols (the bit-sliced decoder takes codes with at most 32; above that k_rs_decode runs)
     bytes_per_unit = 518
 
     def __init__(self, rank, world, total=10**6):
@@ -465,20 +466,32 @@ class RsDecode:
         return self.dec.tensor.view(self.N, 255)
 
     def secondary_roofline(self, units_per_sec):
-        """the decoder is bound by shared-memory table lookups, not HBM.  Field multiply-adds per codeword
-        (one product-table lookup each) against the SM's shared-memory rate of one 32-lane wavefront per clock."""
-        n, d1, v, u = 255, 32, self.n_err, self.n_era
-        ops = d1 * n + (d1 - u) * 2 * (v + 1) + n * (u + v + 1) + (v + u) * (d1 + u + v) + d1 * (v + 1) + d1 * (u + 1) * (u > 0)
+        """the decoder is not HBM-bound.  The bit-sliced kernel (d1 <= 32) is bound by the SM's logic (ALU) pipe:
+        its useful work is the constant-multiply Horner steps of the syndromes and the Chien search, 64 LOP3 warp-instructions
+        per step for 32 codewords, against 4 sub-partitions x one ALU warp-instruction every 2 clocks.  The log-domain kernel
+        (d1 > 32) is bound by shared-memory table lookups: field multiply-adds against one 32-lane wavefront per clock."""
+        n, d1, v, u = 255, self.d1, self.n_err, self.n_era
         sm_mhz = 1965.0
         try:
             sm_mhz = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["sm_max_mhz"])
         except Exception:
             pass
         n_sm = self.torch.cuda.get_device_properties(0).multi_processor_count
+        if d1 <= 32:
+            lop3 = (n + 8 * (u + v + 1)) * 64 / 32.0  # warp-level LOP3 per codeword: syndromes + 8 Chien rounds of 32 positions
+            peak = n_sm * sm_mhz * 1e6 * 4 * 0.5
+            ach = units_per_sec * lop3
+            return {"bound": "alu", "achieved": ach, "peak": peak, "unit": "warp-LOP3/s", "frac": ach / peak,
+                    "ops_per_unit": lop3, "kernel": "k_rs_decode_bs",
+                    "note": "useful logic work only: (n + 8 (u+v+1)) Horner steps x 64 LOP3 per 32 codewords; peak = SMs x 4 "
+                            "sub-partitions x 0.5 ALU-pipe warp-instructions per clock x SM clock.  ncu (profiles/r02_summary.md): "
+                            "ALU pipe 63.5 % active, the busiest unit of the kernel, once the bit transposes, byte packing and "
+                            "the thread-per-codeword key equation are counted"}
+        ops = d1 * n + (d1 - u) * 2 * (v + 1) + n * (u + v + 1) + (v + u) * (d1 + u + v) + d1 * (v + 1) + d1 * (u + 1) * (u > 0)
         peak = n_sm * sm_mhz * 1e6 * 32
         ach = units_per_sec * ops
         return {"bound": "smem", "achieved": ach, "peak": peak, "unit": "GF multiply-add/s", "frac": ach / peak,
-                "ops_per_unit": ops,
+                "ops_per_unit": ops, "kernel": "k_rs_decode",
                 "note": "syndromes d1*n + Berlekamp-Massey + Chien n*(u+v+1) + Forney + the Omega / Gamma products; peak = SMs x 32 lanes x SM clock (one conflict-free shared-memory wavefront per clock)"}
 
     def check(self):
@@ -869,6 +882,7 @@ class BchDecode(RsDecode):
     """Binary BCH(255,131), t = 18: decode 1e6 codewords with 18 bit errors each."""
 
     metric, n_err, n_era, bytes_per_unit = "bch255_131_decode_cw_per_sec", 18, 0, 518
+    kernel, d1 = "k_rs_decode", 36
 
     def __init__(self, rank, world, total=10**6):
         import torch

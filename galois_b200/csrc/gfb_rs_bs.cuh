@@ -66,6 +66,16 @@ __device__ __forceinline__ void build_masks(const uint8_t* __restrict__ T, uint3
     for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(mk[i]));
 }
 
+// the aligned 32-bit word at p, with the bytes outside [lo, hi) read as zero (only the first and the last word of a buffer)
+__device__ __forceinline__ uint32_t load_word_within(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+    if (p >= lo && p + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(p));
+    uint32_t w = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (p + t >= lo && p + t < hi) w |= (uint32_t)p[t] << (8 * t);
+    return w;
+}
+
 // 32 x 32 bit transpose across the warp: on return bit k of lane m is bit m of lane k's input
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
@@ -232,15 +242,26 @@ __device__ __forceinline__ int bm_thread(const uint8_t* __restrict__ T, uint32_t
         if (nn < ls) {
             shift_in_low(Sw, Sq[0] & 255u);
             shift_out_low(Sq);
+            // C, x^m B and the new C have degree <= nn + 1: the words above that are zero and are skipped (uniform branches)
             uint32_t dsc = 0;
 #pragma unroll
-            for (int i = 0; i < 17; ++i) dsc ^= T[row(byte_of(C, i)) ^ byte_of(Sw, i)];
+            for (int j = 0; j < 5; ++j) {
+                if (4 * j <= nn + 1) {
+#pragma unroll
+                    for (int i = 4 * j; i < 4 * j + 4 && i < 17; ++i) dsc ^= T[row(byte_of(C, i)) ^ byte_of(Sw, i)];
+                }
+            }
             const uint32_t rb = row(b), rd = row(dsc);
             uint32_t Cn[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                const uint32_t cn = (uint32_t)T[rb ^ byte_of(C, i)] ^ (uint32_t)T[rd ^ byte_of(Bs, i)];
-                Cn[i >> 2] |= cn << (8 * (i & 3));
+            for (int j = 0; j < 5; ++j) {
+                if (4 * j <= nn + 1) {
+#pragma unroll
+                    for (int i = 4 * j; i < 4 * j + 4 && i < 17; ++i) {
+                        const uint32_t cn = (uint32_t)T[rb ^ byte_of(C, i)] ^ (uint32_t)T[rd ^ byte_of(Bs, i)];
+                        Cn[j] |= cn << (8 * (i & 3));
+                    }
+                }
             }
             const bool grow = dsc != 0 && 2 * L <= nn;
 #pragma unroll
@@ -486,39 +507,49 @@ __global__ void __launch_bounds__(kThreadsPerCta, 1)
                 for (size_t i = lane; i < bytes; i += 32) dst[i] = src[i];
             }
         }
+        // Each lane walks its own row in ALIGNED 32-bit words (one load per four symbols; the row starts at any byte offset, so
+        // neighbouring words are funnel-shifted together); byte m of the row is the symbol of degree ns - 1 - m.  A 32 x 32 bit
+        // transpose across the warp turns one word per lane into the planes of four positions (lane 8 t + j: plane j of byte t).
         uint32_t any_era = 0;
-        for (int i0 = 0; i0 < 256; i0 += 16) {  // ascending degree index, erasures zeroed (_bch.py:1344-1355)
-            uint32_t w[4] = {0, 0, 0, 0};
-            if (mine) {
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {  // sixteen loads in flight
-                    const int i = i0 + t;
-                    const uint32_t b = i < ns ? rrow[ns - 1 - i] : 0u;
-                    w[t >> 2] |= b << (8 * (t & 3));
+        for (int r = 0; r < 8; ++r) PM[32 * r + lane] = 0;
+        __syncwarp();
+        {
+            const int nwords = (ns + 3) >> 2;
+            const int sh = 8 * (int)((uintptr_t)rrow & 3);
+            const uint8_t* pa = rrow - ((uintptr_t)rrow & 3);
+            const uint8_t* ea = erow ? erow - ((uintptr_t)erow & 3) : nullptr;
+            const int esh = erow ? 8 * (int)((uintptr_t)erow & 3) : 0;
+            const uint8_t* r_hi = received + N * (size_t)ns;
+            const uint8_t* e_hi = erasures ? erasures + N * (size_t)ns : nullptr;
+            for (int j0 = 0; j0 < nwords; j0 += 8) {
+                uint32_t W[9], Ew[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {  // the loads of a batch are in flight together
+                    W[t] = (mine && j0 + t <= nwords) ? load_word_within(pa + 4 * (j0 + t), received, r_hi) : 0u;
+                    Ew[t] = (erow && mine && j0 + t <= nwords) ? load_word_within(ea + 4 * (j0 + t), erasures, e_hi) : 0u;
                 }
-            }
-            if (erow) {  // uniform
-                uint32_t ew[4] = {0, 0, 0, 0};
-                if (mine) {
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const int i = i0 + t;
-                        const uint32_t e = (i < ns && erow[ns - 1 - i] != 0) ? 255u : 0u;
-                        ew[t >> 2] |= e << (8 * (t & 3));
+                for (int t = 0; t < 8; ++t) {
+                    const int j = j0 + t;
+                    if (j < nwords) {  // uniform
+                        uint32_t w = __funnelshift_r(W[t], W[t + 1], sh);
+                        const int m = 4 * j + (lane >> 3);  // the row byte this lane holds after the transpose
+                        if (erow) {  // uniform: erased symbols are zeroed (_bch.py:1344-1355)
+                            const uint32_t e = __funnelshift_r(Ew[t], Ew[t + 1], esh);
+                            const uint32_t nz = (((e & 0x7f7f7f7fu) + 0x7f7f7f7fu) | e) & 0x80808080u;  // bit 7 of every non-zero byte
+                            const uint32_t em8 = (nz >> 7) * 255u;
+                            w &= ~em8;
+                            const uint32_t em = transpose32(em8, lane);
+                            const bool hit = m < ns && em != 0;
+                            any_era |= __ballot_sync(0xffffffffu, hit);
+                            if (m < ns && (lane & 7) == 0) PM[ns - 1 - m] = em;
+                        }
+                        const uint32_t planes = transpose32(w, lane);
+                        if (m < ns) R[(ns - 1 - m) * 8 + (lane & 7)] = planes;
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    w[q] &= ~ew[q];
-                    const uint32_t em = transpose32(ew[q], lane);  // lane 8t: erasure mask of position i0 + 4q + t
-                    any_era |= __ballot_sync(0xffffffffu, em != 0);
-                    if ((lane & 7) == 0) PM[i0 + 4 * q + (lane >> 3)] = em;
-                }
-            } else {
-                if (lane < 16) PM[i0 + lane] = 0;
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) R[(i0 + 4 * q) * 8 + lane] = transpose32(w[q], lane);  // lane 8t + j: plane j of position + t
         }
         __syncwarp();
         // ---- 2. syndromes S_l = r(alpha^(c+l)), lane l, all 32 codewords at once (:1370)

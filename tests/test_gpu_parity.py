@@ -663,3 +663,46 @@ def test_ufunc_methods_reduce_accumulate_reduceat_at(name):
         np.negative.reduce(gx)
     with pytest.raises(ValueError):
         np.power.accumulate(gx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ns,offset,N", [(255, 1, 97), (255, 3, 64), (200, 2, 45), (64, 1, 33), (33, 0, 32)])
+def test_rs_decode_unaligned_buffers_vs_oracle(ns, offset, N):
+    """The bit-sliced decoder reads each row in aligned words: device buffers that start at any byte offset, shortened codes
+    (rows of ns < n symbols), a partial last group and erasures must give the oracle's rows bit for bit."""
+    import torch
+
+    from galois_b200 import _lib
+    from galois_b200._field import DeviceArray
+
+    rs = gb.ReedSolomon(255, 223)
+    F = oracle.Field.binary(8, 0x11D, alpha=2)
+    ors = oracle.ReedSolomon(F, 255, 223)
+    ks = ns - 32
+    rng = np.random.default_rng(1000 + ns + offset)
+    M = rng.integers(0, 256, (N, ks), dtype=np.uint8)
+    C = ors.encode(M)
+    R = C.copy()
+    E = np.zeros(R.shape, dtype=bool)
+    for i in range(N):
+        n_era = int(rng.integers(0, 9)) if i % 3 else 0
+        n_err = int(rng.integers(0, (32 - n_era) // 2 + 2))  # some rows beyond the correction radius
+        pos = rng.choice(ns, min(ns, n_err + n_era), replace=False)
+        R[i, pos[:n_err]] ^= rng.integers(1, 256, len(pos[:n_err])).astype(np.uint8)
+        E[i, pos[n_err:]] = True
+    for use_era in (False, True):
+        odec, onerr = ors.decode(R, E if use_era else None, threads=4)
+        buf_r = torch.zeros(N * ns + 8, dtype=torch.uint8, device="cuda")
+        buf_e = torch.zeros(N * ns + 8, dtype=torch.uint8, device="cuda")
+        buf_o = torch.zeros(N * ns + 8, dtype=torch.uint8, device="cuda")
+        buf_r[offset:offset + N * ns] = torch.from_numpy(R.reshape(-1)).cuda()
+        buf_e[offset + 1:offset + 1 + N * ns] = torch.from_numpy(E.reshape(-1).astype(np.uint8)).cuda()
+        nerr = torch.empty(N, dtype=torch.int64, device="cuda")
+        st = _lib.lib().gfb_rs_decode(rs._code(), buf_r.data_ptr() + offset, buf_e.data_ptr() + offset + 1 if use_era else None, ns,
+                                      buf_o.data_ptr() + offset, nerr.data_ptr(), N, DeviceArray._stream())
+        _lib.check(st, "gfb_rs_decode")
+        torch.cuda.synchronize()
+        got = buf_o[offset:offset + N * ns].cpu().numpy().reshape(N, ns)
+        assert np.array_equal(nerr.cpu().numpy(), onerr), (ns, offset, use_era)
+        assert np.array_equal(got, odec), (ns, offset, use_era)
+        assert int(buf_o[:offset].sum()) == 0 and int(buf_o[offset + N * ns:].sum()) == 0  # nothing written outside the rows
