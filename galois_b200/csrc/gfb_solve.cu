@@ -26,7 +26,11 @@
 //   k_lu_pivot    (1 CTA)   find the pivot, exchange; publish the pivot row (rowbuf) and the column multipliers (colbuf)
 //   k_eliminate   (grid)    A[r][c] -= colbuf[r] * rowbuf[c] for the rows below, columns c >= i, 256 columns x 32 rows per CTA
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
+
+#include <cooperative_groups.h>
 
 #include "gfb_common.cuh"
 #include "gfb_dispatch.cuh"
@@ -324,7 +328,9 @@ k_rr_panel_w(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw
 constexpr int kUpdCols = 128;
 constexpr int kUpdRows = 16;
 
-template <typename T, typename F>
+// SMALLP: a prime below 2^30 — sixteen products fit one 64-bit accumulator, so a multiply-add is ONE IMAD.WIDE instead of a
+// 128-bit add-with-carry chain (the kernel is bound by the integer-multiply pipe: ncu, profiles/r02_summary.md).
+template <typename T, typename F, bool SMALLP = false>
 __global__ void __launch_bounds__(kUpdCols)
 k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw,
                   const PanelMeta* __restrict__ meta, const typename F::elem* __restrict__ M,
@@ -352,15 +358,412 @@ k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, i
         const size_t r = r0 + rr;
         if (r >= rows) break;
         if (r >= (size_t)p0 && r < (size_t)p1) continue;  // pivot rows were finished by k_rr_panel_w
-        DotAcc<F> acc;
-        acc.init(f);
+        E d;
+        if constexpr (SMALLP) {
+            unsigned long long s0 = 0ull, s1 = 0ull;
 #pragma unroll
-        for (int t = 0; t < kPanel; ++t) acc.fma(f, s_m[rr][t], w[t]);
-        const E d = acc.done(f);
+            for (int t = 0; t < kPanel / 2; ++t) {
+                s0 += (unsigned long long)s_m[rr][t] * w[t];
+                s1 += (unsigned long long)s_m[rr][t + kPanel / 2] * w[t + kPanel / 2];
+            }
+            d = f.add(f.reduce64(s0), f.reduce64(s1));
+        } else {
+            DotAcc<F> acc;
+            acc.init(f);
+#pragma unroll
+            for (int t = 0; t < kPanel; ++t) acc.fma(f, s_m[rr][t], w[t]);
+            d = acc.done(f);
+        }
         if (!f.is_zero(d)) {
             const size_t idx = r * cols + c;
             A[idx] = to_store<T, E>(f.sub(to_elem<E, T>(A[idx]), d));
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- row_reduce: cluster panel
+// The panel step spread over a thread-block cluster (fields whose elements fit 32 bits, up to 4096 rows).  k_rr_panel above
+// is one CTA walking a shared-memory slab: every column step pays a Fermat inversion of the pivot on one thread (~1 us), five
+// CTA barriers and a read-modify-write pass over the slab — 4.4 us per step, 142 us per 32-column panel of a 1024-row matrix,
+// two thirds of the whole elimination.  Here
+//   * eight CTAs x 128 threads form one cluster; every thread keeps its row(s) of the slab IN REGISTERS (32 entries each,
+//     rotated by one register per step so that the current column is always entry 0 — no dynamic register indexing);
+//   * rows are never moved: each row carries its logical position, an exchange swaps two integers;
+//   * the pivot search is a warp min + one distributed-shared-memory atomicMin per warp into every CTA's copy, the owner's
+//     warp pushes the pivot row (32 values) into every CTA's shared memory, two cluster barriers per step;
+//   * the steps are FRACTION-FREE: row_r <- piv * row_r - a[r][s] * row_p (every row but the pivot row, which is only
+//     scaled), so no inversion sits on the critical path.  All rows then share the scale c(s) = prod of the earlier scaled
+//     pivots, the entry a[r][s] a row holds when column s is eliminated is c(s) times the multiplier the textbook step would
+//     use (times the true pivot of row r's own step when r already is a pivot row), and the 65 inversions that undo the
+//     scaling (c(s), the scaled pivots, the final scale) run in parallel once per panel.  The row-reduced form is unique,
+//     and the multipliers / pivots / exchange records written for the trailing kernels are exactly the textbook ones.
+//   * the trailing columns do not replay the 32-step recurrence per column (k_rr_panel_w: a 55 us dependent chain on 14
+//     SMs): the panel also emits the two 32 x 32 matrices T (w = T x: the scaled pivot-row entries the steps used) and
+//     T2 (the final pivot rows = T2 x) and k_rr_panel_w2 applies them as 64 independent dot products per column.
+namespace cgx = cooperative_groups;
+constexpr int kClCtas = 8;
+constexpr int kClThreads = 128;
+constexpr int kClRows = kClCtas * kClThreads;
+
+template <typename T, typename F, int RPT>
+__global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads)
+k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, ElimState* st, PanelMeta* meta,
+                   typename F::elem* __restrict__ M, typename F::elem* __restrict__ TT, size_t fs) {
+    using E = typename F::elem;
+    static_assert(sizeof(E) == 4, "the cluster panel keeps 32-bit field elements in registers");
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    __shared__ int s_min[2];
+    __shared__ E s_prow[2][kPanel];  // pivot row of the step in flight, multiplier form (every CTA has its own copy)
+    __shared__ E s_piv[2];           // its (scaled) pivot
+    __shared__ E s_pivs[kPanel], s_cs[kPanel], s_cinv[kPanel], s_pinvt[kPanel];
+    __shared__ E s_cendinv;
+    __shared__ int s_pp[kPanel], s_pi[kPanel];
+    __shared__ E s_mp[kPanel][kPanel + 1];  // rank 0: s_mp[s][t] = multiplier of pivot row s at step t
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    E a[RPT][kPanel];
+    int pos[RPT], stp[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const size_t r = (size_t)k * kClRows + (size_t)rank * kClThreads + tid;
+        stp[k] = -1;
+        if (r < rows) {
+            pos[k] = (int)r;
+#pragma unroll
+            for (int t = 0; t < kPanel; ++t) a[k][t] = t < kw ? to_elem<E, T>(A[r * cols + j0 + t]) : f.zero();
+        } else {
+            pos[k] = INT_MAX;
+#pragma unroll
+            for (int t = 0; t < kPanel; ++t) a[k][t] = f.zero();
+        }
+    }
+    if (tid < 2) s_min[tid] = INT_MAX;
+    for (int idx = tid; idx < kPanel * (kPanel + 1); idx += kClThreads) (&s_mp[0][0])[idx] = f.zero();
+    int p = st->p;
+    const int p0 = p;
+    E c = f.one();
+    uint32_t nullmask = 0;
+    int swaps = 0;
+    cluster.sync();  // every CTA's s_min is initialised before the first remote atomic
+
+    for (int s = 0; s < kPanel; ++s) {
+        if (s < kw) {  // uniform
+            const int b = s & 1;
+            // first non-zero entry of column s at or below logical row p
+            int cand = INT_MAX;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (!f.is_zero(a[k][0]) && pos[k] >= p && pos[k] < cand) cand = pos[k];
+            cand = __reduce_min_sync(0xffffffffu, cand);
+            if (lane == 0 && cand != INT_MAX) {
+#pragma unroll
+                for (int r = 0; r < kClCtas; ++r) atomicMin(cluster.map_shared_rank(&s_min[b], r), cand);
+            }
+            cluster.sync();
+            const int i = s_min[b];
+            if (tid == 0) s_min[b ^ 1] = INT_MAX;  // for step s + 1: its atomics start after the second barrier below
+            if (i != INT_MAX) {
+                bool own[RPT];
+                bool own_any = false;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    own[k] = pos[k] == i;
+                    own_any |= own[k];
+                }
+                const uint32_t ow = __ballot_sync(0xffffffffu, own_any);
+                if (ow) {  // the owner's warp publishes the pivot row: lane L takes column L and writes it to every CTA
+                    const int ol = __ffs(ow) - 1;
+                    E mine = f.zero();
+#pragma unroll
+                    for (int u = 0; u < kPanel; ++u) {
+                        E v = f.zero();
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k)
+                            if (own[k]) v = a[k][u];
+                        const E got = __shfl_sync(0xffffffffu, v, ol);
+                        if (lane == ((s + u) & 31)) mine = got;
+                    }
+                    const E pm = f.premul(mine);
+#pragma unroll
+                    for (int r = 0; r < kClCtas; ++r) {
+                        *cluster.map_shared_rank(&s_prow[b][lane], r) = pm;
+                        if (lane == (s & 31)) *cluster.map_shared_rank(&s_piv[b], r) = mine;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {  // the exchange of logical rows p and i
+                    if (own[k]) {
+                        pos[k] = p;
+                        stp[k] = s;
+                    } else if (pos[k] == p) {
+                        pos[k] = i;
+                    }
+                }
+            }
+            cluster.sync();
+            if (i != INT_MAX) {
+                const E piv = s_piv[b];
+                const E pivP = f.premul(piv);
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const bool is_piv_row = stp[k] == s;
+                    const E m = a[k][0];
+                    // entry u is column (s + u) mod 32: it changes when that is a later column or an earlier one that had no
+                    // pivot.  Groups of eight entries behind one uniform branch, selects inside: the eight updates of a group
+                    // are independent instruction streams (a branch per entry serialises them — with one warp per scheduler
+                    // nothing else hides the latency).
+#pragma unroll
+                    for (int g = 0; g < kPanel / 8; ++g) {
+                        if (8 * g <= kPanel - 1 - s || nullmask != 0u) {  // uniform
+#pragma unroll
+                            for (int u = (g == 0 ? 1 : 8 * g); u < 8 * g + 8; ++u) {
+                                const bool need = u <= kPanel - 1 - s || ((nullmask >> ((s + u) & 31)) & 1u);
+                                const E x = f.mul_prepared(a[k][u], pivP);
+                                const E y = is_piv_row ? x : f.sub(x, f.mul_prepared(m, s_prow[b][(s + u) & 31]));
+                                a[k][u] = need ? y : a[k][u];
+                            }
+                        }
+                    }
+                    if (is_piv_row) a[k][0] = f.zero();  // its own multiplier
+                }
+                if (tid == 0) {
+                    s_pivs[s] = piv;
+                    s_cs[s] = c;
+                    s_pp[s] = p;
+                    s_pi[s] = i;
+                }
+                c = f.mul(c, piv);
+                swaps += i != p ? 1 : 0;
+                ++p;
+            } else {
+                if (tid == 0) {
+                    s_pivs[s] = f.zero();
+                    s_cs[s] = c;
+                    s_pp[s] = -1;
+                    s_pi[s] = -1;
+                }
+                nullmask |= 1u << s;
+            }
+        } else if (tid == 0) {
+            s_pivs[s] = f.zero();
+            s_cs[s] = c;
+            s_pp[s] = -1;
+            s_pi[s] = -1;
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {  // rotate: the next column moves to entry 0, the finished one to the end
+            const E first = a[k][0];
+#pragma unroll
+            for (int u = 0; u < kPanel - 1; ++u) a[k][u] = a[k][u + 1];
+            a[k][kPanel - 1] = first;
+        }
+    }
+    __syncthreads();
+    // undo the scaling: 1 / c(s), the true pivot inverses c(s) / piv'(s), 1 / c(end) — 65 independent inversions
+    if (tid < kPanel) {
+        s_cinv[tid] = f.inv1(s_cs[tid]);
+    } else if (tid < 2 * kPanel) {
+        const int s = tid - kPanel;
+        s_pinvt[s] = s_pp[s] >= 0 ? f.mul(s_cs[s], f.inv1(s_pivs[s])) : f.zero();
+    } else if (tid == 2 * kPanel) {
+        s_cendinv = f.inv1(c);
+    }
+    __syncthreads();
+    if (rank == 0 && tid == 0) {
+        E det = (E)st->det;
+        for (int s = 0; s < kw; ++s)
+            if (s_pp[s] >= 0) det = f.mul(det, f.mul(s_pivs[s], s_cinv[s]));
+        st->det = (unsigned long long)det;
+        st->p = p;
+        st->n_swaps += swaps;
+        meta->p0 = p0;
+        meta->p1 = p;
+        for (int s = 0; s < kw; ++s) {
+            meta->piv_p[s] = s_pp[s];
+            meta->piv_i[s] = s_pi[s];
+            meta->pinv[s] = (unsigned long long)s_pinvt[s];
+        }
+    }
+    // textbook multipliers and the finished panel columns, each row at its logical position
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        if (pos[k] == INT_MAX) continue;
+        const size_t r = (size_t)pos[k];
+        const E mine_pinv = stp[k] >= 0 ? s_pinvt[stp[k]] : f.one();
+#pragma unroll
+        for (int t = 0; t < kPanel; ++t) {
+            if (t < kw) {  // uniform
+                E mult = f.zero(), entry;
+                if (s_pp[t] >= 0) {  // uniform
+                    mult = f.mul(a[k][t], s_cinv[t]);
+                    if (stp[k] >= 0 && stp[k] < t) mult = f.mul(mult, mine_pinv);
+                    entry = stp[k] == t ? f.one() : f.zero();
+                } else {
+                    entry = f.mul(a[k][t], s_cendinv);
+                    if (stp[k] >= 0) entry = f.mul(entry, mine_pinv);
+                }
+                M[r * kPanel + t] = mult;
+                A[r * cols + j0 + t] = to_store<T, E>(entry);
+                if (stp[k] >= 0) *cluster.map_shared_rank(&s_mp[stp[k]][t], 0) = mult;
+            }
+        }
+    }
+    cluster.sync();
+    if (rank != 0) return;
+    // T: w_s = pinv_s (x_s - sum_{t<s} mp[s][t] w_t) as a matrix on x; T2 = (I - strict upper part of mp) T.  Rolled loops over
+    // shared memory (unrolling the 32 x 32 recurrence is ~200 KB of straight-line code that runs at instruction-fetch speed);
+    // thread (column j, quarter q): each row's dot product is split over the four warps.
+    __shared__ E s_T[kPanel][kPanel + 1];
+    __shared__ E s_part[4][kPanel];
+    const int j = tid & 31, q = tid >> 5;
+#pragma unroll 1
+    for (int s = 0; s < kPanel; ++s) {
+        DotAcc<F> acc;
+        acc.init(f);
+        for (int t = q; t < s; t += 4) acc.fma(f, s_mp[s][t], s_T[t][j]);
+        s_part[q][j] = acc.done(f);
+        __syncthreads();
+        if (q == 0) {
+            const E sum = f.add(f.add(s_part[0][j], s_part[1][j]), f.add(s_part[2][j], s_part[3][j]));
+            const E v = s_pp[s] >= 0 ? f.mul(s_pinvt[s], f.sub(j == s ? f.one() : f.zero(), sum)) : f.zero();
+            s_T[s][j] = v;
+            TT[s * kPanel + j] = v;
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int e = 0; e < kPanel / 4; ++e) {
+        const int s = q * (kPanel / 4) + e;
+        DotAcc<F> acc;
+        acc.init(f);
+#pragma unroll 4
+        for (int t = s + 1; t < kPanel; ++t) acc.fma(f, s_mp[s][t], s_T[t][j]);
+        TT[kPanel * kPanel + s * kPanel + j] = f.sub(s_T[s][j], acc.done(f));
+    }
+}
+
+// Trailing columns after the cluster panel: exchange replay (as k_rr_panel_w), then w = T x (stored for the update kernel)
+// and the finished pivot rows T2 x, x = the 32 pivot-row entries of the column.  One CTA per 32 columns; thread (column,
+// quarter) computes eight rows of both products.
+constexpr int kW2Cols = 32;
+constexpr int kW2Threads = 128;
+
+template <typename T, typename F, bool SMALLP = false>
+__global__ void __launch_bounds__(kW2Threads)
+k_rr_panel_w2(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw, const PanelMeta* __restrict__ meta,
+              const typename F::elem* __restrict__ TT, typename F::elem* __restrict__ W, size_t fs) {
+    using E = typename F::elem;
+    extern __shared__ uint4 smem_raw[];
+    f.init_smem(smem_raw);
+    (void)fs;
+    (void)rows;
+    __shared__ E s_T[kPanel][kPanel + 1], s_T2[kPanel][kPanel + 1], s_x[kPanel][kW2Cols + 1];
+    __shared__ int s_p[kPanel], s_i[kPanel];
+    __shared__ int s_pos[2 * kPanel], s_src[2 * kPanel], s_moves;
+    if (meta->p1 == meta->p0) return;  // the panel found no pivot: nothing changes (uniform)
+    for (int idx = threadIdx.x; idx < kPanel * kPanel; idx += blockDim.x) {
+        const int s = idx / kPanel, j = idx - s * kPanel;
+        s_T[s][j] = TT[idx];
+        s_T2[s][j] = TT[kPanel * kPanel + idx];
+    }
+    if (threadIdx.x < kPanel) {
+        const int s = threadIdx.x;
+        s_p[s] = s < kw ? meta->piv_p[s] : -1;
+        s_i[s] = s < kw ? meta->piv_i[s] : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // net effect of the exchanges: position s_pos[k] ends up holding the row that started at s_src[k]
+        int n = 0;
+        for (int s = 0; s < kw; ++s) {
+            const int ps = s_p[s], is = s_i[s];
+            if (ps < 0 || is == ps) continue;
+            int kp = -1, ki = -1;
+            for (int k = 0; k < n; ++k) {
+                if (s_pos[k] == ps) kp = k;
+                if (s_pos[k] == is) ki = k;
+            }
+            if (kp < 0) {
+                kp = n++;
+                s_pos[kp] = ps;
+                s_src[kp] = ps;
+            }
+            if (ki < 0) {
+                ki = n++;
+                s_pos[ki] = is;
+                s_src[ki] = is;
+            }
+            const int t = s_src[kp];
+            s_src[kp] = s_src[ki];
+            s_src[ki] = t;
+        }
+        s_moves = n;
+    }
+    __syncthreads();
+    const int col = threadIdx.x & (kW2Cols - 1), q = threadIdx.x / kW2Cols;  // q = 0..3
+    const size_t c = c0 + (size_t)blockIdx.x * kW2Cols + col;
+    const bool live = c < cols;
+    {
+        const int n = s_moves;
+        T v[2 * kPanel / 4];
+#pragma unroll
+        for (int e = 0; e < 2 * kPanel / 4; ++e) {
+            const int k = q + 4 * e;
+            if (live && k < n) v[e] = A[(size_t)s_src[k] * cols + c];
+        }
+        __syncthreads();  // every load of the exchange before any store
+#pragma unroll
+        for (int e = 0; e < 2 * kPanel / 4; ++e) {
+            const int k = q + 4 * e;
+            if (live && k < n && s_src[k] != s_pos[k]) A[(size_t)s_pos[k] * cols + c] = v[e];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < kPanel / 4; ++e) {
+        const int s = q * (kPanel / 4) + e;
+        s_x[s][col] = (live && s_p[s] >= 0) ? to_elem<E, T>(A[(size_t)s_p[s] * cols + c]) : f.zero();
+    }
+    __syncthreads();
+    if (!live) return;
+#pragma unroll 1
+    for (int e = 0; e < kPanel / 4; ++e) {
+        const int s = q * (kPanel / 4) + e;
+        if (s >= kw) break;
+        E w = f.zero();
+        if (s_p[s] >= 0) {  // uniform per warp
+            E y;
+            if constexpr (SMALLP) {  // p < 2^30: sixteen products per 64-bit accumulator (see k_rr_panel_update)
+                unsigned long long w0 = 0ull, w1 = 0ull, y0 = 0ull, y1 = 0ull;
+#pragma unroll 8
+                for (int j = 0; j < kPanel / 2; ++j) {
+                    const unsigned long long x0 = s_x[j][col], x1 = s_x[j + kPanel / 2][col];
+                    w0 += x0 * s_T[s][j];
+                    w1 += x1 * s_T[s][j + kPanel / 2];
+                    y0 += x0 * s_T2[s][j];
+                    y1 += x1 * s_T2[s][j + kPanel / 2];
+                }
+                w = f.add(f.reduce64(w0), f.reduce64(w1));
+                y = f.add(f.reduce64(y0), f.reduce64(y1));
+            } else {
+                DotAcc<F> aw, ay;
+                aw.init(f);
+                ay.init(f);
+#pragma unroll 8
+                for (int j = 0; j < kPanel; ++j) {
+                    const E x = s_x[j][col];
+                    aw.fma(f, s_T[s][j], x);
+                    ay.fma(f, s_T2[s][j], x);
+                }
+                w = aw.done(f);
+                y = ay.done(f);
+            }
+            A[(size_t)s_p[s] * cols + c] = to_store<T, E>(y);
+        }
+        W[(size_t)s * cols + c] = w;
     }
 }
 
@@ -496,6 +899,7 @@ struct ElimWorkspace {
     PanelMeta* meta;
     void* M;  // rows x kPanel multipliers
     void* W;  // kPanel x cols scaled pivot-row entries
+    void* TT; // the two kPanel x kPanel matrices of the cluster panel (T, T2)
 };
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -514,12 +918,14 @@ static ElimWorkspace carve(void* ws, size_t rows, size_t cols) {
     w.M = base;
     base += align16(rows * kPanel * 8);
     w.W = base;
+    base += align16(cols * kPanel * 8);
+    w.TT = base;
     return w;
 }
 
 static size_t elim_workspace_bytes(size_t rows, size_t cols) {
     return 64 + align16(cols * 8) + align16(rows * 8) + align16(sizeof(PanelMeta)) + align16(rows * kPanel * 8) +
-           align16(cols * kPanel * 8) + 64;
+           align16(cols * kPanel * 8) + 2 * kPanel * kPanel * 8 + 64;
 }
 
 static dim3 elim_grid(size_t rows, size_t cols, size_t c0) {
@@ -559,15 +965,64 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
             if (slab_in_smem)
                 GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)(fs + slab_bytes)));
+            // fields with 32-bit elements, up to 4096 rows: the panel runs on a thread-block cluster (k_rr_panel_cluster)
+            // and the trailing pivot rows come from its T / T2 matrices (k_rr_panel_w2).  GFB_ELIM_CLUSTER=0 keeps the
+            // single-CTA panel (the tests run both and compare).
+            bool use_cluster = false;
+            if constexpr (sizeof(E) == 4) {
+                const char* env = getenv("GFB_ELIM_CLUSTER");  // read per call: the tests switch it inside one process
+                const bool cluster_on = !(env && env[0] == '0');
+                use_cluster = cluster_on && rows <= (size_t)4 * kClRows && fs <= (size_t)160 * 1024;
+            }
             for (size_t j0 = 0; j0 < ncols; j0 += kPanel) {
                 const int kw = (int)(ncols - j0 < (size_t)kPanel ? ncols - j0 : (size_t)kPanel);
+                const size_t c0 = j0 + kw;  // trailing columns
+                if constexpr (sizeof(E) == 4) {
+                    if (use_cluster) {
+                        if (rows <= (size_t)kClRows) {
+                            if (fs > 48 * 1024)
+                                GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 1>,
+                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                            k_rr_panel_cluster<T, F, 1><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
+                                                                                          w.meta, (E*)w.M, (E*)w.TT, fs);
+                        } else {
+                            if (fs > 48 * 1024)
+                                GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 4>,
+                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                            k_rr_panel_cluster<T, F, 4><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
+                                                                                          w.meta, (E*)w.M, (E*)w.TT, fs);
+                        }
+                        if (c0 < cols) {
+                            const unsigned gw = (unsigned)((cols - c0 + kW2Cols - 1) / kW2Cols);
+                            bool small_p = false;
+                            if constexpr (std::is_same_v<F, PrimeBarrett>) small_p = functor.p < (1u << 30);
+                            if constexpr (std::is_same_v<F, PrimeBarrett>) {
+                                if (small_p)
+                                    k_rr_panel_w2<T, F, true><<<gw, kW2Threads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                                          (const E*)w.TT, (E*)w.W, fs);
+                            }
+                            if (!small_p)
+                                k_rr_panel_w2<T, F><<<gw, kW2Threads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                                (const E*)w.TT, (E*)w.W, fs);
+                            dim3 gu((unsigned)((cols - c0 + kUpdCols - 1) / kUpdCols), (unsigned)((rows + kUpdRows - 1) / kUpdRows));
+                            if constexpr (std::is_same_v<F, PrimeBarrett>) {
+                                if (small_p)
+                                    k_rr_panel_update<T, F, true><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                                            (const E*)w.M, (const E*)w.W, fs);
+                            }
+                            if (!small_p)
+                                k_rr_panel_update<T, F><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                                                                                  (const E*)w.M, (const E*)w.W, fs);
+                        }
+                        continue;
+                    }
+                }
                 if (slab_in_smem)
                     k_rr_panel<T, F, true><<<1, kPivotThreads, fs + slab_bytes, st>>>(functor, (T*)A, rows, cols, j0, kw,
                                                                                        w.state, w.meta, (E*)w.M, fs);
                 else
                     k_rr_panel<T, F, false><<<1, kPivotThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
                                                                            w.meta, (E*)w.M, fs);
-                const size_t c0 = j0 + kw;  // trailing columns
                 if (c0 < cols) {
                     const unsigned gw = (unsigned)((cols - c0 + kPanelWThreads - 1) / kPanelWThreads);
                     k_rr_panel_w<T, F><<<gw, kPanelWThreads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
