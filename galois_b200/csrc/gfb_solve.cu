@@ -28,6 +28,7 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include <cooperative_groups.h>
@@ -332,7 +333,7 @@ constexpr int kUpdRows = 16;
 // 128-bit add-with-carry chain (the kernel is bound by the integer-multiply pipe: ncu, profiles/r02_summary.md).
 template <typename T, typename F, bool SMALLP = false>
 __global__ void __launch_bounds__(kUpdCols)
-k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw,
+k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, size_t c_end, int kw,
                   const PanelMeta* __restrict__ meta, const typename F::elem* __restrict__ M,
                   const typename F::elem* __restrict__ W, size_t fs) {
     using E = typename F::elem;
@@ -350,7 +351,7 @@ k_rr_panel_update(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, i
     }
     __syncthreads();
     const size_t c = c0 + (size_t)blockIdx.x * kUpdCols + threadIdx.x;
-    if (c >= cols) return;
+    if (c >= c_end) return;  // columns [c0, c_end)
     E w[kPanel];
 #pragma unroll
     for (int t = 0; t < kPanel; ++t) w[t] = t < kw ? W[(size_t)t * cols + c] : f.zero();
@@ -450,20 +451,31 @@ k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, 
     int swaps = 0;
     cluster.sync();  // every CTA's s_min is initialised before the first remote atomic
 
+    // One step = search barrier, owner's push, push barrier, update.  The search of step s + 1 is software-pipelined into
+    // step s: the next column (entry 1) is updated first, its candidates are sent and the search barrier is ARRIVED at
+    // before the other 30 entries are updated, so that barrier's latency hides behind the update.
+    auto post_candidate = [&](E (&col)[RPT], int p_now, int buf) {
+        int cand = INT_MAX;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+            if (!f.is_zero(col[k]) && pos[k] >= p_now && pos[k] < cand) cand = pos[k];
+        cand = __reduce_min_sync(0xffffffffu, cand);
+        if (lane == 0 && cand != INT_MAX) {
+#pragma unroll
+            for (int r = 0; r < kClCtas; ++r) atomicMin(cluster.map_shared_rank(&s_min[buf], r), cand);
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    };
+    if (kw > 0) {
+        E col[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) col[k] = a[k][0];
+        post_candidate(col, p, 0);
+    }
     for (int s = 0; s < kPanel; ++s) {
         if (s < kw) {  // uniform
             const int b = s & 1;
-            // first non-zero entry of column s at or below logical row p
-            int cand = INT_MAX;
-#pragma unroll
-            for (int k = 0; k < RPT; ++k)
-                if (!f.is_zero(a[k][0]) && pos[k] >= p && pos[k] < cand) cand = pos[k];
-            cand = __reduce_min_sync(0xffffffffu, cand);
-            if (lane == 0 && cand != INT_MAX) {
-#pragma unroll
-                for (int r = 0; r < kClCtas; ++r) atomicMin(cluster.map_shared_rank(&s_min[b], r), cand);
-            }
-            cluster.sync();
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // the search of column s is complete
             const int i = s_min[b];
             if (tid == 0) s_min[b ^ 1] = INT_MAX;  // for step s + 1: its atomics start after the second barrier below
             if (i != INT_MAX) {
@@ -505,27 +517,41 @@ k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, 
                 }
             }
             cluster.sync();
-            if (i != INT_MAX) {
-                const E piv = s_piv[b];
-                const E pivP = f.premul(piv);
+            const bool found = i != INT_MAX;
+            E piv = f.zero(), pivP = f.zero();
+            // entry u is column (s + u) mod 32: it changes when that is a later column or an earlier one that had no pivot
+            auto update_entry = [&](int k, int u, E m, bool is_piv_row, E cur) -> E {
+                const bool need = u <= kPanel - 1 - s || ((nullmask >> ((s + u) & 31)) & 1u);
+                const E x = f.mul_prepared(cur, pivP);
+                const E y = is_piv_row ? x : f.sub(x, f.mul_prepared(m, s_prow[b][(s + u) & 31]));
+                return need ? y : cur;
+            };
+            if (found) {
+                piv = s_piv[b];
+                pivP = f.premul(piv);
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) a[k][1] = update_entry(k, 1, a[k][0], stp[k] == s, a[k][1]);
+            }
+            if (s + 1 < kw) {  // uniform: the search of column s + 1 starts now
+                E col[RPT];
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) col[k] = a[k][1];
+                post_candidate(col, found ? p + 1 : p, b ^ 1);
+            }
+            if (found) {
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
                     const bool is_piv_row = stp[k] == s;
                     const E m = a[k][0];
-                    // entry u is column (s + u) mod 32: it changes when that is a later column or an earlier one that had no
-                    // pivot.  Groups of eight entries behind one uniform branch, selects inside: the eight updates of a group
-                    // are independent instruction streams (a branch per entry serialises them — with one warp per scheduler
-                    // nothing else hides the latency).
+                    // groups of eight entries behind one uniform branch, selects inside: the updates of a group are
+                    // independent instruction streams (a branch per entry serialises them — with one warp per scheduler
+                    // nothing else hides the latency)
 #pragma unroll
                     for (int g = 0; g < kPanel / 8; ++g) {
                         if (8 * g <= kPanel - 1 - s || nullmask != 0u) {  // uniform
 #pragma unroll
-                            for (int u = (g == 0 ? 1 : 8 * g); u < 8 * g + 8; ++u) {
-                                const bool need = u <= kPanel - 1 - s || ((nullmask >> ((s + u) & 31)) & 1u);
-                                const E x = f.mul_prepared(a[k][u], pivP);
-                                const E y = is_piv_row ? x : f.sub(x, f.mul_prepared(m, s_prow[b][(s + u) & 31]));
-                                a[k][u] = need ? y : a[k][u];
-                            }
+                            for (int u = (g == 0 ? 2 : 8 * g); u < 8 * g + 8; ++u)
+                                a[k][u] = update_entry(k, u, m, is_piv_row, a[k][u]);
                         }
                     }
                     if (is_piv_row) a[k][0] = f.zero();  // its own multiplier
@@ -654,8 +680,9 @@ constexpr int kW2Threads = 128;
 
 template <typename T, typename F, bool SMALLP = false>
 __global__ void __launch_bounds__(kW2Threads)
-k_rr_panel_w2(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int kw, const PanelMeta* __restrict__ meta,
-              const typename F::elem* __restrict__ TT, typename F::elem* __restrict__ W, size_t fs) {
+k_rr_panel_w2(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, size_t c_end, int kw,
+              const PanelMeta* __restrict__ meta, const typename F::elem* __restrict__ TT, typename F::elem* __restrict__ W,
+              size_t fs) {
     using E = typename F::elem;
     extern __shared__ uint4 smem_raw[];
     f.init_smem(smem_raw);
@@ -705,7 +732,7 @@ k_rr_panel_w2(F f, T* __restrict__ A, size_t rows, size_t cols, size_t c0, int k
     __syncthreads();
     const int col = threadIdx.x & (kW2Cols - 1), q = threadIdx.x / kW2Cols;  // q = 0..3
     const size_t c = c0 + (size_t)blockIdx.x * kW2Cols + col;
-    const bool live = c < cols;
+    const bool live = c < c_end;  // columns [c0, c_end)
     {
         const int n = s_moves;
         T v[2 * kPanel / 4];
@@ -900,6 +927,11 @@ struct ElimWorkspace {
     void* M;  // rows x kPanel multipliers
     void* W;  // kPanel x cols scaled pivot-row entries
     void* TT; // the two kPanel x kPanel matrices of the cluster panel (T, T2)
+    // second set for the pipelined cluster path: panel k + 1 is factored while the far trailing columns still read panel k's
+    PanelMeta* meta2;
+    void* M2;
+    void* W2;
+    void* TT2;
 };
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -920,11 +952,56 @@ static ElimWorkspace carve(void* ws, size_t rows, size_t cols) {
     w.W = base;
     base += align16(cols * kPanel * 8);
     w.TT = base;
+    base += 2 * kPanel * kPanel * 8;
+    w.meta2 = (PanelMeta*)base;
+    base += align16(sizeof(PanelMeta));
+    w.M2 = base;
+    base += align16(rows * kPanel * 8);
+    w.W2 = base;
+    base += align16(cols * kPanel * 8);
+    w.TT2 = base;
     return w;
+}
+
+// side stream + events of the pipelined cluster elimination (one set per process and device; enqueueing is serialised)
+struct ElimSide {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+    cudaError_t ensure() {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (stream && dev == device) return cudaSuccess;
+        if (stream) {  // another device became current: rebuild on it
+            cudaStreamDestroy(stream);
+            for (int i = 0; i < 2; ++i) {
+                cudaEventDestroy(ev_panel[i]);
+                cudaEventDestroy(ev_b[i]);
+            }
+            stream = nullptr;
+        }
+        e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < 2; ++i) {
+            e = cudaEventCreateWithFlags(&ev_panel[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&ev_b[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        device = dev;
+        return cudaSuccess;
+    }
+};
+static ElimSide& elim_side() {
+    static ElimSide s;
+    return s;
 }
 
 static size_t elim_workspace_bytes(size_t rows, size_t cols) {
     return 64 + align16(cols * 8) + align16(rows * 8) + align16(sizeof(PanelMeta)) + align16(rows * kPanel * 8) +
+           align16(cols * kPanel * 8) + 2 * kPanel * kPanel * 8 + align16(sizeof(PanelMeta)) + align16(rows * kPanel * 8) +
            align16(cols * kPanel * 8) + 2 * kPanel * kPanel * 8 + 64;
 }
 
@@ -974,49 +1051,73 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
                 const bool cluster_on = !(env && env[0] == '0');
                 use_cluster = cluster_on && rows <= (size_t)4 * kClRows && fs <= (size_t)160 * 1024;
             }
-            for (size_t j0 = 0; j0 < ncols; j0 += kPanel) {
+            if constexpr (sizeof(E) == 4) {
+                if (use_cluster) {
+                    // Pipelined: after panel k only the columns of panel k + 1 are updated on the caller's stream (part a);
+                    // the far trailing columns (part b) run on a side stream WHILE panel k + 1 is factored on its 8 SMs.
+                    // meta / M / W / TT alternate between two sets so that part b of panel k and panel k + 1 never share one.
+                    ElimSide& side = elim_side();
+                    std::lock_guard<std::mutex> lock(side.mu);
+                    GFB_CUDA_TRY(side.ensure());
+                    bool small_p = false;
+                    if constexpr (std::is_same_v<F, PrimeBarrett>) small_p = functor.p < (1u << 30);
+                    auto trailing = [&](cudaStream_t s2, size_t cb, size_t ce, int kw, int q) {
+                        if (cb >= ce) return;
+                        PanelMeta* meta = q ? w.meta2 : w.meta;
+                        const E* Mq = (const E*)(q ? w.M2 : w.M);
+                        E* Wq = (E*)(q ? w.W2 : w.W);
+                        const E* TTq = (const E*)(q ? w.TT2 : w.TT);
+                        const unsigned gw = (unsigned)((ce - cb + kW2Cols - 1) / kW2Cols);
+                        dim3 gu((unsigned)((ce - cb + kUpdCols - 1) / kUpdCols), (unsigned)((rows + kUpdRows - 1) / kUpdRows));
+                        if constexpr (std::is_same_v<F, PrimeBarrett>) {
+                            if (small_p) {
+                                k_rr_panel_w2<T, F, true><<<gw, kW2Threads, fs, s2>>>(functor, (T*)A, rows, cols, cb, ce, kw, meta, TTq, Wq, fs);
+                                k_rr_panel_update<T, F, true><<<gu, kUpdCols, fs, s2>>>(functor, (T*)A, rows, cols, cb, ce, kw, meta, Mq, Wq, fs);
+                                return;
+                            }
+                        }
+                        k_rr_panel_w2<T, F><<<gw, kW2Threads, fs, s2>>>(functor, (T*)A, rows, cols, cb, ce, kw, meta, TTq, Wq, fs);
+                        k_rr_panel_update<T, F><<<gu, kUpdCols, fs, s2>>>(functor, (T*)A, rows, cols, cb, ce, kw, meta, Mq, Wq, fs);
+                    };
+                    if (fs > 48 * 1024) {
+                        GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                        GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                    }
+                    bool side_used = false;
+                    size_t k = 0;
+                    for (size_t j0 = 0; j0 < ncols; j0 += kPanel, ++k) {
+                        const int kw = (int)(ncols - j0 < (size_t)kPanel ? ncols - j0 : (size_t)kPanel);
+                        const int q = (int)(k & 1);
+                        PanelMeta* meta = q ? w.meta2 : w.meta;
+                        E* Mq = (E*)(q ? w.M2 : w.M);
+                        E* TTq = (E*)(q ? w.TT2 : w.TT);
+                        if (rows <= (size_t)kClRows)
+                            k_rr_panel_cluster<T, F, 1><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                        else
+                            k_rr_panel_cluster<T, F, 4><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                        const size_t c0 = j0 + kw;  // trailing columns [c0, cols)
+                        const bool more = c0 < ncols;  // another panel follows: its columns are [c0, c0 + 32)
+                        const size_t ca = more ? (c0 + kPanel < cols ? c0 + kPanel : cols) : cols;
+                        // part b of the previous panel also covers [c0, cols): it must be finished before part a touches them
+                        if (side_used) GFB_CUDA_TRY(cudaStreamWaitEvent(st, side.ev_b[q ^ 1], 0));
+                        if (more && ca < cols) {
+                            GFB_CUDA_TRY(cudaEventRecord(side.ev_panel[q], st));
+                            GFB_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.ev_panel[q], 0));
+                            trailing(side.stream, ca, cols, kw, q);
+                            GFB_CUDA_TRY(cudaEventRecord(side.ev_b[q], side.stream));
+                            side_used = true;
+                            trailing(st, c0, ca, kw, q);
+                        } else {
+                            side_used = false;
+                            trailing(st, c0, cols, kw, q);
+                        }
+                    }
+                    if (side_used) GFB_CUDA_TRY(cudaStreamWaitEvent(st, side.ev_b[(int)((k - 1) & 1)], 0));
+                }
+            }
+            for (size_t j0 = 0; j0 < ncols && !use_cluster; j0 += kPanel) {
                 const int kw = (int)(ncols - j0 < (size_t)kPanel ? ncols - j0 : (size_t)kPanel);
                 const size_t c0 = j0 + kw;  // trailing columns
-                if constexpr (sizeof(E) == 4) {
-                    if (use_cluster) {
-                        if (rows <= (size_t)kClRows) {
-                            if (fs > 48 * 1024)
-                                GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 1>,
-                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-                            k_rr_panel_cluster<T, F, 1><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
-                                                                                          w.meta, (E*)w.M, (E*)w.TT, fs);
-                        } else {
-                            if (fs > 48 * 1024)
-                                GFB_CUDA_TRY(cudaFuncSetAttribute(k_rr_panel_cluster<T, F, 4>,
-                                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-                            k_rr_panel_cluster<T, F, 4><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state,
-                                                                                          w.meta, (E*)w.M, (E*)w.TT, fs);
-                        }
-                        if (c0 < cols) {
-                            const unsigned gw = (unsigned)((cols - c0 + kW2Cols - 1) / kW2Cols);
-                            bool small_p = false;
-                            if constexpr (std::is_same_v<F, PrimeBarrett>) small_p = functor.p < (1u << 30);
-                            if constexpr (std::is_same_v<F, PrimeBarrett>) {
-                                if (small_p)
-                                    k_rr_panel_w2<T, F, true><<<gw, kW2Threads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
-                                                                                          (const E*)w.TT, (E*)w.W, fs);
-                            }
-                            if (!small_p)
-                                k_rr_panel_w2<T, F><<<gw, kW2Threads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
-                                                                                (const E*)w.TT, (E*)w.W, fs);
-                            dim3 gu((unsigned)((cols - c0 + kUpdCols - 1) / kUpdCols), (unsigned)((rows + kUpdRows - 1) / kUpdRows));
-                            if constexpr (std::is_same_v<F, PrimeBarrett>) {
-                                if (small_p)
-                                    k_rr_panel_update<T, F, true><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
-                                                                                            (const E*)w.M, (const E*)w.W, fs);
-                            }
-                            if (!small_p)
-                                k_rr_panel_update<T, F><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
-                                                                                  (const E*)w.M, (const E*)w.W, fs);
-                        }
-                        continue;
-                    }
-                }
                 if (slab_in_smem)
                     k_rr_panel<T, F, true><<<1, kPivotThreads, fs + slab_bytes, st>>>(functor, (T*)A, rows, cols, j0, kw,
                                                                                        w.state, w.meta, (E*)w.M, fs);
@@ -1028,7 +1129,7 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
                     k_rr_panel_w<T, F><<<gw, kPanelWThreads, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
                                                                        (const E*)w.M, (E*)w.W, fs);
                     dim3 gu((unsigned)((cols - c0 + kUpdCols - 1) / kUpdCols), (unsigned)((rows + kUpdRows - 1) / kUpdRows));
-                    k_rr_panel_update<T, F><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, kw, w.meta,
+                    k_rr_panel_update<T, F><<<gu, kUpdCols, fs, st>>>(functor, (T*)A, rows, cols, c0, cols, kw, w.meta,
                                                                       (const E*)w.M, (const E*)w.W, fs);
                 }
             }
