@@ -934,7 +934,7 @@ class MatInv:
     """inverse of a 1024 x 1024 matrix over GF(998244353) by row-reducing [A | I] (inv_jit)."""
 
     metric, unit, dtype, scaling = "gfp_matinv_1024_per_sec", "inv/s", "uint32", "weak"
-    kernel = "k_eliminate (+ k_rr_pivot per column)"
+    kernel = "k_rr_panel_cluster (+ k_rr_panel_w2, k_rr_panel_update per 32-column panel)"
     n = 1024
     bytes_per_unit = 2 * 4 * 1024 * 1024  # compulsory: read A, write A^-1 (the n^3 update traffic is the algorithm's own)
 
@@ -955,7 +955,7 @@ class MatInv:
         self.src = gb.DeviceArray(self.GF, ai.view(torch.uint8).reshape(-1), (n, 2 * n), np.uint32)
         self.out = gb.DeviceArray.empty(self.GF, (n, 2 * n), np.uint32)
         self.units_per_step = 1
-        self.launches_per_step = 2 * n + 2
+        self.launches_per_step = 5 * (n // 32) + 2  # panel + (w2, update) on the next panel's columns and on the far columns
         self.h2d = self.d2h = 0
 
     def step(self):

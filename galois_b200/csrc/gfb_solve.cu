@@ -406,7 +406,11 @@ constexpr int kClCtas = 8;
 constexpr int kClThreads = 128;
 constexpr int kClRows = kClCtas * kClThreads;
 
-template <typename T, typename F, int RPT>
+// ODDP (PrimeBarrett only): the prime is odd, products go straight to the Montgomery step.  mul_prepared() tests p == 2 on
+// every call and the compiler keeps that as a (uniform) branch: one convergence region per entry of the register update, no
+// overlap between the 31 independent updates of a step — with one warp per scheduler the step then runs at one dependent
+// instruction per ~6 clocks (ncu: profiles/r02_elim_cluster.md).
+template <typename T, typename F, int RPT, bool ODDP = false>
 __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads)
 k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, int kw, ElimState* st, PanelMeta* meta,
                    typename F::elem* __restrict__ M, typename F::elem* __restrict__ TT, size_t fs) {
@@ -520,17 +524,23 @@ k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, 
             const bool found = i != INT_MAX;
             E piv = f.zero(), pivP = f.zero();
             // entry u is column (s + u) mod 32: it changes when that is a later column or an earlier one that had no pivot
+            auto mulp = [&](E x, E y_prepared) -> E {
+                if constexpr (ODDP)
+                    return f.montmul(x, y_prepared);
+                else
+                    return f.mul_prepared(x, y_prepared);
+            };
             auto update_entry = [&](int k, int u, E m, bool is_piv_row, E cur) -> E {
                 const bool need = u <= kPanel - 1 - s || ((nullmask >> ((s + u) & 31)) & 1u);
-                const E x = f.mul_prepared(cur, pivP);
-                const E y = is_piv_row ? x : f.sub(x, f.mul_prepared(m, s_prow[b][(s + u) & 31]));
+                (void)is_piv_row;  // the pivot row comes in with m = 0: it is only scaled (no branch inside the entry)
+                const E y = f.sub(mulp(cur, pivP), mulp(m, s_prow[b][(s + u) & 31]));
                 return need ? y : cur;
             };
             if (found) {
                 piv = s_piv[b];
                 pivP = f.premul(piv);
 #pragma unroll
-                for (int k = 0; k < RPT; ++k) a[k][1] = update_entry(k, 1, a[k][0], stp[k] == s, a[k][1]);
+                for (int k = 0; k < RPT; ++k) a[k][1] = update_entry(k, 1, stp[k] == s ? f.zero() : a[k][0], stp[k] == s, a[k][1]);
             }
             if (s + 1 < kw) {  // uniform: the search of column s + 1 starts now
                 E col[RPT];
@@ -542,7 +552,7 @@ k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, 
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
                     const bool is_piv_row = stp[k] == s;
-                    const E m = a[k][0];
+                    const E m = is_piv_row ? f.zero() : a[k][0];
                     // groups of eight entries behind one uniform branch, selects inside: the updates of a group are
                     // independent instruction streams (a branch per entry serialises them — with one warp per scheduler
                     // nothing else hides the latency)
@@ -614,28 +624,37 @@ k_rr_panel_cluster(F f, T* __restrict__ A, size_t rows, size_t cols, size_t j0, 
             meta->pinv[s] = (unsigned long long)s_pinvt[s];
         }
     }
-    // textbook multipliers and the finished panel columns, each row at its logical position
+    // textbook multipliers and the finished panel columns, each row at its logical position.  A rolled loop over the columns
+    // (the registers rotate as in the steps): unrolled, this block is ~10 k instructions that run once per launch at
+    // instruction-fetch speed.
+    E mine_pinv[RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-        if (pos[k] == INT_MAX) continue;
-        const size_t r = (size_t)pos[k];
-        const E mine_pinv = stp[k] >= 0 ? s_pinvt[stp[k]] : f.one();
+    for (int k = 0; k < RPT; ++k) mine_pinv[k] = stp[k] >= 0 ? s_pinvt[stp[k]] : f.one();
+#pragma unroll 1
+    for (int t = 0; t < kPanel; ++t) {
+        if (t < kw) {  // uniform
+            const bool piv_col = s_pp[t] >= 0;  // uniform
+            const E scale = piv_col ? s_cinv[t] : s_cendinv;
 #pragma unroll
-        for (int t = 0; t < kPanel; ++t) {
-            if (t < kw) {  // uniform
-                E mult = f.zero(), entry;
-                if (s_pp[t] >= 0) {  // uniform
-                    mult = f.mul(a[k][t], s_cinv[t]);
-                    if (stp[k] >= 0 && stp[k] < t) mult = f.mul(mult, mine_pinv);
-                    entry = stp[k] == t ? f.one() : f.zero();
-                } else {
-                    entry = f.mul(a[k][t], s_cendinv);
-                    if (stp[k] >= 0) entry = f.mul(entry, mine_pinv);
+            for (int k = 0; k < RPT; ++k) {
+                if (pos[k] != INT_MAX) {
+                    const size_t r = (size_t)pos[k];
+                    E v = f.mul(a[k][0], scale);
+                    if (stp[k] >= 0 && (!piv_col || stp[k] < t)) v = f.mul(v, mine_pinv[k]);
+                    const E mult = piv_col ? v : f.zero();
+                    const E entry = piv_col ? (stp[k] == t ? f.one() : f.zero()) : v;
+                    M[r * kPanel + t] = mult;
+                    A[r * cols + j0 + t] = to_store<T, E>(entry);
+                    if (stp[k] >= 0) *cluster.map_shared_rank(&s_mp[stp[k]][t], 0) = mult;
                 }
-                M[r * kPanel + t] = mult;
-                A[r * cols + j0 + t] = to_store<T, E>(entry);
-                if (stp[k] >= 0) *cluster.map_shared_rank(&s_mp[stp[k]][t], 0) = mult;
             }
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const E first = a[k][0];
+#pragma unroll
+            for (int u = 0; u < kPanel - 1; ++u) a[k][u] = a[k][u + 1];
+            a[k][kPanel - 1] = first;
         }
     }
     cluster.sync();
@@ -1091,10 +1110,20 @@ gfb_status gfb_row_reduce(gfb_field* f, int eb, void* A, size_t rows, size_t col
                         PanelMeta* meta = q ? w.meta2 : w.meta;
                         E* Mq = (E*)(q ? w.M2 : w.M);
                         E* TTq = (E*)(q ? w.TT2 : w.TT);
-                        if (rows <= (size_t)kClRows)
-                            k_rr_panel_cluster<T, F, 1><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
-                        else
-                            k_rr_panel_cluster<T, F, 4><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                        bool odd_p = false;
+                        if constexpr (std::is_same_v<F, PrimeBarrett>) odd_p = (functor.p & 1u) != 0;
+                        if constexpr (std::is_same_v<F, PrimeBarrett>) {
+                            if (odd_p && rows <= (size_t)kClRows)
+                                k_rr_panel_cluster<T, F, 1, true><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                            else if (odd_p)
+                                k_rr_panel_cluster<T, F, 4, true><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                        }
+                        if (!odd_p) {
+                            if (rows <= (size_t)kClRows)
+                                k_rr_panel_cluster<T, F, 1><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                            else
+                                k_rr_panel_cluster<T, F, 4><<<kClCtas, kClThreads, fs, st>>>(functor, (T*)A, rows, cols, j0, kw, w.state, meta, Mq, TTq, fs);
+                        }
                         const size_t c0 = j0 + kw;  // trailing columns [c0, cols)
                         const bool more = c0 < ncols;  // another panel follows: its columns are [c0, c0 + 32)
                         const size_t ca = more ? (c0 + kPanel < cols ? c0 + kPanel : cols) : cols;

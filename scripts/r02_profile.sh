@@ -19,4 +19,7 @@ capture ntt k_ntt_fused 1 1 --workload ntt --batch 592 --steps 2 --warmup 3
 capture rs k_rs_decode 3 1 --workload rs_decode --batch 200000 --steps 3 --warmup 3
 capture gf256 k_tab8_aa 3 1 --workload gf256_mul --steps 3 --warmup 3
 capture gf128 k_binary 3 1 --workload gf2_128_mul --steps 3 --warmup 3
+capture elim k_rr_panel_cluster 12 1 --workload matinv --steps 1 --warmup 1
+ncu -i /tmp/prof/elim.ncu-rep --page source --csv > $OUT/${TAG}_elim_source.csv 2>/dev/null
+ncu -i /tmp/prof/rs.ncu-rep --page source --csv > $OUT/${TAG}_rs_source.csv 2>/dev/null
 ls -la $OUT | grep ${TAG}_

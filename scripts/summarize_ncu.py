@@ -43,8 +43,8 @@ def main(tag):
              "cold-cache and serialised: use them for shares and per-launch traffic, not as benchmark values.", ""]
     traffic = {}
     workload_of = {"mul": "gfp_mul", "ntt": "ntt", "rs": "rs_decode", "gf128": "gf2_128_mul", "gf256": "gf256_mul",
-                   "ntt_fused": "ntt"}
-    for name in ("mul", "ntt", "rs", "gf256", "gf128"):
+                   "ntt_fused": "ntt", "elim": "matinv_panel"}
+    for name in ("mul", "ntt", "rs", "gf256", "gf128", "elim"):
         fn = SRC / f"{tag}_{name}_raw.csv"
         if not fn.exists():
             continue
@@ -52,9 +52,9 @@ def main(tag):
         det = SRC / f"{tag}_{name}_details.csv"
         if det.exists():
             shutil.copy(det, DST / det.name)
-        lines += [f"## {name}", "", "| kernel | time | dram read | dram write | regs | warps active % | issue active % | SM thr % | inst (warp) | smem bank conflicts / wavefronts |", "|---|---|---|---|---|---|---|---|---|---|"]
+        lines += [f"## {name}", "", "| kernel | time | dram read | dram write | regs | warps active % | issue active % | SM thr % | ALU pipe % | FMA-heavy pipe % | inst (warp) | smem bank conflicts / wavefronts |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
         tot = 0.0
-        units = {"mul": 10**8, "rs": 200000, "gf128": 10**7, "gf256": 10**8}.get(name)  # elements / codewords per captured launch
+        units = {"mul": 10**8, "rs": 200000, "gf128": 10**7, "gf256": 10**8, "elim": 1}.get(name)  # elements / codewords per captured launch
         for d, u in raw_rows(fn):
             if name in ("ntt", "ntt_fused"):
                 if "fused" in d["Kernel Name"]:
@@ -69,7 +69,10 @@ def main(tag):
             lines.append(f"| `{kn}` | {t*1e6:.1f} us | {rd/1e6:.1f} MB | {wr/1e6:.1f} MB | {d['launch__registers_per_thread']} | "
                          f"{float(d['sm__warps_active.avg.pct_of_peak_sustained_active']):.1f} | "
                          f"{float(d['smsp__issue_active.avg.pct_of_peak_sustained_active']):.1f} | "
-                         f"{float(d['sm__throughput.avg.pct_of_peak_sustained_elapsed']):.1f} | {float(d['smsp__inst_executed.sum']):.3g} | "
+                         f"{float(d['sm__throughput.avg.pct_of_peak_sustained_elapsed']):.1f} | "
+                         f"{float(d.get('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active') or 0):.1f} | "
+                         f"{float(d.get('sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed') or 0):.1f} | "
+                         f"{float(d['smsp__inst_executed.sum']):.3g} | "
                          f"{d['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']} / {d['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']} |")
         # dram bytes of the captured launch(es) (ntt: pass 1 + pass 2 of one chunk) and the units they processed
         traffic[workload_of[name]] = {"dram_bytes": tot, "units": units, "dram_bytes_per_unit": tot / units}
