@@ -333,7 +333,7 @@ class Ntt:
     """BASELINE configs[2]: 2^20-point NTT over GF(998244353), batch 4096 sharded over the ranks (strong)."""
 
     metric, unit, dtype, scaling = "ntt_2p20_per_sec", "NTT/s", "uint32", "strong"
-    kernel = "k_ntt_pass1 + k_ntt_pass2"
+    kernel = "k_ntt_fused (persistent, TMA-staged; GFB_NTT_FUSED=0: k_ntt_pass1 + k_ntt_pass2)"
     N = 2**20
     bytes_per_unit = 2 * 4 * 2**20  # 8 MiB per transform (SURVEY.md §8d)
 
