@@ -218,7 +218,11 @@ gfb_status gfb_matmul_host(gfb_field* f, int elem_bytes, const void* A, const vo
  *   info (device, 2 x int64): [0] = number of pivots p, [1] = number of row exchanges.
  *   det  (device, elem_bytes, may be NULL): (-1)^exchanges x product of the pivots — det(A) when A is square,
  *        ncols == cols and p == rows (the value det_jit :446-471 computes through PLU; 0 otherwise is the caller's job).
- * The device variant needs gfb_row_reduce_workspace_bytes() of scratch.  Fields wider than 64 bits: UNSUPPORTED. */
+ * The device variant needs gfb_row_reduce_workspace_bytes() of scratch.  Fields wider than 64 bits: UNSUPPORTED.
+ * Fields whose elements fit 32 bits, up to 4096 rows: the 32-column panel runs on a thread-block cluster and the far
+ * trailing columns of a panel are updated on an internal side stream while the next panel is factored; the side stream
+ * is joined back into `stream` before the call returns, so the caller sees ordinary stream semantics
+ * (GFB_ELIM_CLUSTER=0 keeps the single-CTA panel). */
 size_t gfb_row_reduce_workspace_bytes(const gfb_field* f, size_t rows, size_t cols);
 gfb_status gfb_row_reduce(gfb_field* f, int elem_bytes, void* A, size_t rows, size_t cols, size_t ncols,
                           int64_t* info, void* det, void* workspace, void* stream);
@@ -260,7 +264,9 @@ gfb_status gfb_rs_encode(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* c
                          void* stream);
 /* Errors-and-erasures decode: received [N][ns] (+ optional erasure mask [N][ns], bytes 0/1, may
  * be NULL) → corrected codewords [N][ns] and n_errors [N] (int64; -1 = uncorrectable, row left
- * equal to the received row).  bch_decode_jit.implementation (_codes/_bch.py:1337-1578). */
+ * equal to the received row).  bch_decode_jit.implementation (_codes/_bch.py:1337-1578).
+ * Codes with at most 32 parity symbols and N >= 32 run the bit-sliced kernel (32 codewords per warp); the buffers may
+ * start at any byte offset.  GFB_RS_DECODER=log|fast|bs selects a kernel explicitly (same results). */
 gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t* erasures, int ns,
                          uint8_t* decoded, int64_t* n_errors, size_t N, void* stream);
 gfb_status gfb_rs_encode_host(gfb_rs_code* rs, const uint8_t* msg, int ks, uint8_t* codeword,

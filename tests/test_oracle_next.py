@@ -144,3 +144,28 @@ def test_live_linalg_next(live_next):
                 with pytest.raises(np.linalg.LinAlgError) as ei:
                     F.matrix_inv(A)
                 assert str(ei.value) == str(data[f"{b}/inv_raises"]), b
+
+
+def test_oracle_prime_field_above_int64_products():
+    """p > ~3.03e9: a * b exceeds 2^63 (the reference leaves int64 for Python integers there, _fields/_factory.py dtypes).  The
+    oracle multiplies in 128 bits; checked against Python big integers, element-wise and through the elimination."""
+    p = 4294967291
+    F = oracle.Field.prime(p)
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, p, 2000)
+    b = rng.integers(1, p, 2000)
+    assert [int(x) for x in F.mul(a, b)] == [int(x) * int(y) % p for x, y in zip(a, b)]
+    assert [int(x) for x in F.mul(F.div(a, b), b)] == [int(x) for x in a]
+    A = rng.integers(0, p, (7, 40))
+    A[6] = A[0]
+    R, n_piv = F.row_reduce(A, 33)
+    assert n_piv == 6 and int(R.max()) < p and int(R.min()) >= 0
+    # the reduced rows span the same space: every original row is a combination of them (checked with big integers)
+    piv_cols = [int(np.flatnonzero(R[i])[0]) for i in range(n_piv)]
+    for row in A:
+        acc = [0] * 40
+        for i, c in enumerate(piv_cols):
+            f = int(row[c])
+            for j in range(40):
+                acc[j] = (acc[j] + f * int(R[i, j])) % p
+        assert acc == [int(x) for x in row]
