@@ -707,7 +707,7 @@ gfb_status gfb_rs_decode(gfb_rs_code* rs, const uint8_t* received, const uint8_t
     // GFB_RS_FAST=1 selects the register-resident decoder of gfb_rs_fast.cuh.  Measured on a B200 (1e6 RS(255,223) words x 16
     // errors): 1.14e8 cw/s against 1.21e8 for k_rs_decode below — it halves the instruction count but its product-table
     // lookups make it shared-memory-wavefront bound (ncu: 82 % of the cycles, 3.4-way conflicts on data-dependent byte
-    // loads), so the log-domain kernel stays the default.
+    // loads), so it is not selected by default (the bit-sliced kernel above is).
     static const bool fast_on = [] {
         const char* e = getenv("GFB_RS_FAST");
         return (e && e[0] == '1');
